@@ -1,0 +1,193 @@
+"""Oracle restatement of the generation loop (TEST INFRASTRUCTURE ONLY).
+
+Follows:
+  Qwen3TTS::generate_codes             src/lib.rs:530-656
+  StreamingSession::{from_prefill,next_chunk}  src/lib.rs:1584-1759
+  codes_to_tensor                      src/lib.rs:1417-1431
+  decode_codes                         src/lib.rs:881-890
+  synthesize_with_voice / _voice_design  src/lib.rs:718-784, 802-870
+
+Batch semantics: the reference has no batching (SURVEY.md "where the north star and the
+reference disagree" #2); a batch of B utterances is B independent runs of this loop.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import sampling as smp
+from .model import CodePredictor, Talker, Prec
+
+
+def codes_to_tensor(codes: Sequence[Sequence[int]]) -> np.ndarray:
+    """lib.rs:1417-1431: [n_frames][16] -> i64 [1,16,T], data[q*T + f]."""
+    n = len(codes)
+    out = np.zeros((1, 16, n), dtype=np.int64)
+    for f, frame in enumerate(codes):
+        for q, c in enumerate(frame):
+            out[0, q, f] = c
+    return out
+
+
+class Trace:
+    """Per-frame intermediates for teacher-forced comparison with the CUDA path."""
+
+    def __init__(self):
+        self.frames: List[dict] = []
+
+
+def sample_first(talker: Talker, logits: torch.Tensor, cfg: smp.GenerationConfig, ctx: smp.SamplingContext,
+                 penalty_mask: np.ndarray, suppression: np.ndarray, logit_hook=None):
+    """lib.rs:557-571: sample token 0 with token_count = 0."""
+    l2 = logits[:, 0].numpy().astype(np.float32)
+    if logit_hook is not None:
+        l2 = logit_hook(-1, l2)
+    l2 = smp.apply_generation_penalties(l2, penalty_mask, cfg, 0, suppression)
+    tok = int(smp.sample(l2, cfg, ctx)[0])
+    smp.update_penalty_mask(penalty_mask, tok)
+    return tok
+
+
+def generate_codes(talker: Talker, cp: CodePredictor, cfg: smp.GenerationConfig, ctx: smp.SamplingContext,
+                   kv_caches, offset: int, last_hidden: torch.Tensor, initial_logits: torch.Tensor,
+                   trailing_text_hidden: torch.Tensor, trailing_text_len: int, tts_pad_embed: torch.Tensor,
+                   trace: Optional[Trace] = None,
+                   logit_hook: Optional[Callable[[int, np.ndarray], np.ndarray]] = None) -> List[List[int]]:
+    """lib.rs:530-656.  `logit_hook(frame_idx, logits_f32[1,V])` lets a test force EOS at a chosen
+    frame by editing the raw talker logits before penalties."""
+    p: Prec = talker.p
+    vocab = talker.spec.codec_vocab
+    suppression = smp.build_suppression_mask(vocab, 2150)
+    penalty_mask = np.zeros((1, vocab), dtype=np.float32)
+    cp_caches = cp.new_kv_caches()
+
+    tok = sample_first(talker, initial_logits, cfg, ctx, penalty_mask, suppression, logit_hook)
+    token_count = 1
+    frames: List[List[int]] = []
+    for frame_idx in range(cfg.max_new_tokens):
+        if cfg.eos_token_id is not None and tok == cfg.eos_token_id:      # lib.rs:581-585
+            break
+        sem = talker.codec_embed([tok])                                   # lib.rs:588-590
+        if trace is not None:
+            codes, cp_logits = cp.generate_acoustic_codes(last_hidden, sem, cp_caches, return_logits=True)
+        else:
+            codes = cp.generate_acoustic_codes(last_hidden, sem, cp_caches)
+        frames.append([tok] + codes)                                      # lib.rs:605-609
+        summed = p.r(sem + cp.acoustic_embeddings_sum(codes))             # lib.rs:612-615
+        if frame_idx < trailing_text_len:                                 # lib.rs:617-621
+            text_add = trailing_text_hidden[:, frame_idx: frame_idx + 1]
+        else:
+            text_add = tts_pad_embed
+        step_input = p.r(summed + text_add)
+        h, logits = talker.generate_step_with_embed(step_input, kv_caches, offset)   # lib.rs:627-631
+        offset += 1
+        raw = logits[:, 0].numpy().astype(np.float32)
+        if logit_hook is not None:
+            raw = logit_hook(frame_idx, raw)
+        l2 = smp.apply_generation_penalties(raw, penalty_mask, cfg, token_count, suppression)
+        rng_state_before = ctx.state
+        next_tok = int(smp.sample(l2, cfg, ctx)[0])
+        if trace is not None:
+            trace.frames.append(dict(frame=frame_idx, tok=tok, codes=codes, cp_in_hidden=last_hidden.clone(),
+                                     cp_logits=cp_logits, step_input=step_input.clone(), hidden=h.clone(),
+                                     logits=raw.copy(), penalised=l2.copy(), rng_state=rng_state_before,
+                                     next_tok=next_tok))
+        last_hidden = h
+        tok = next_tok
+        smp.update_penalty_mask(penalty_mask, tok)
+        token_count += 1
+    return frames
+
+
+def prefill_and_generate(talker: Talker, cp: CodePredictor, prefill_embeds: torch.Tensor,
+                         text_ids: Sequence[int], cfg: smp.GenerationConfig, seed: int,
+                         trace: Optional[Trace] = None, logit_hook=None, kv_max: Optional[int] = None):
+    """synthesize_with_voice minus tokenizer and vocoder (lib.rs:743-777)."""
+    ctx = smp.SamplingContext(seed)
+    trailing, tlen, pad = talker.build_trailing_text(text_ids)
+    caches = talker.new_kv_caches(kv_max if kv_max is not None else cfg.max_new_tokens + 256)
+    hidden, logits = talker.run_prefill_layers(prefill_embeds, caches)
+    plen = hidden.shape[1]
+    last_hidden = hidden[:, plen - 1: plen]
+    return generate_codes(talker, cp, cfg, ctx, caches, plen, last_hidden, logits, trailing, tlen, pad,
+                          trace=trace, logit_hook=logit_hook)
+
+
+class StreamingSession:
+    """StreamingSession (lib.rs:1484-1782): same per-frame body; every `chunk_frames` frames the
+    buffered codes are decoded INDEPENDENTLY (no vocoder state crosses chunks, lib.rs:1755-1758)."""
+
+    def __init__(self, talker: Talker, cp: CodePredictor, decode_fn, prefill_embeds: torch.Tensor,
+                 text_ids: Sequence[int], cfg: smp.GenerationConfig, seed: int, chunk_frames: int = 10):
+        self.talker, self.cp, self.decode_fn, self.cfg = talker, cp, decode_fn, cfg
+        self.ctx = smp.SamplingContext(seed)
+        self.trailing, self.tlen, self.pad = talker.build_trailing_text(text_ids)
+        self.caches = talker.new_kv_caches(cfg.max_new_tokens + 256)
+        hidden, logits = talker.run_prefill_layers(prefill_embeds, self.caches)
+        plen = hidden.shape[1]
+        self.offset = plen
+        self.last_hidden = hidden[:, plen - 1: plen]
+        vocab = talker.spec.codec_vocab
+        self.suppression = smp.build_suppression_mask(vocab, 2150)
+        self.penalty_mask = np.zeros((1, vocab), dtype=np.float32)
+        first = sample_first(talker, logits, cfg, self.ctx, self.penalty_mask, self.suppression)
+        self.done = cfg.eos_token_id == first                          # lib.rs:1621
+        self.current_token = None if self.done else first
+        self.frames_generated = 0
+        self.frame_buffer: List[List[int]] = []
+        self.chunk_frames = chunk_frames
+        self.token_count = 1
+        self.cp_caches = cp.new_kv_caches()
+        self.all_frames: List[List[int]] = []
+
+    def next_chunk(self):
+        """lib.rs:1650-1759. Returns PCM ndarray or None."""
+        p = self.talker.p
+        if self.done:
+            if self.frame_buffer:
+                buf, self.frame_buffer = self.frame_buffer, []
+                return self.decode_fn(codes_to_tensor(buf))
+            return None
+        while len(self.frame_buffer) < self.chunk_frames and self.frames_generated < self.cfg.max_new_tokens:
+            if self.current_token is None:
+                self.done = True
+                break
+            tok = self.current_token
+            sem = self.talker.codec_embed([tok])
+            codes = self.cp.generate_acoustic_codes(self.last_hidden, sem, self.cp_caches)
+            self.frame_buffer.append([tok] + codes)
+            self.all_frames.append([tok] + codes)
+            frame_idx = self.frames_generated
+            self.frames_generated += 1
+            summed = p.r(sem + self.cp.acoustic_embeddings_sum(codes))
+            text_add = self.trailing[:, frame_idx: frame_idx + 1] if frame_idx < self.tlen else self.pad
+            step_input = p.r(summed + text_add)
+            h, logits = self.talker.generate_step_with_embed(step_input, self.caches, self.offset)
+            self.offset += 1
+            self.last_hidden = h
+            l2 = smp.apply_generation_penalties(logits[:, 0].numpy().astype(np.float32), self.penalty_mask,
+                                                self.cfg, self.token_count, self.suppression)
+            nxt = int(smp.sample(l2, self.cfg, self.ctx)[0])
+            smp.update_penalty_mask(self.penalty_mask, nxt)
+            self.token_count += 1
+            if self.cfg.eos_token_id == nxt:                            # lib.rs:1740-1747
+                self.current_token = None
+                self.done = True
+            else:
+                self.current_token = nxt
+        if not self.frame_buffer:
+            return None
+        buf, self.frame_buffer = self.frame_buffer, []
+        return self.decode_fn(codes_to_tensor(buf))
+
+    def is_done(self):
+        return self.done and not self.frame_buffer
+
+    def __iter__(self):
+        while True:
+            c = self.next_chunk()
+            if c is None:
+                return
+            yield c
