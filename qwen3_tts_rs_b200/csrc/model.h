@@ -1,0 +1,101 @@
+// Host-side model / session objects behind the opaque C handles.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+struct DBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DBuf() = default;
+  DBuf(const DBuf&) = delete;
+  DBuf& operator=(const DBuf&) = delete;
+  DBuf(DBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DBuf& operator=(DBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    Q3_CHECK_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  void ensure(size_t n) { if (n > bytes) alloc(n); }
+  void zero(cudaStream_t st = 0) { if (p) Q3_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, st)); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct RawTensor {
+  DBuf buf;
+  std::vector<int64_t> shape;
+  q3_dtype dtype;
+  size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
+};
+
+// ---- talker / code predictor ---------------------------------------------------------------------
+struct LayerW {
+  const bf16 *in_ln, *wqkv, *wo, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
+};
+struct StackDims { int H, I, heads, kv_heads, layers; };
+
+// ---- vocoder ----------------------------------------------------------------------------------------
+struct VConv { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, k = 1; };
+struct VSnake { const float* ea = nullptr; const float* ib = nullptr; };
+struct VLayer { const float *in_ln, *post_ln, *attn_scale, *mlp_scale; VConv q, k, v, o, gate, up, down; };
+struct VConvNext { const float *dw_w, *dw_b, *ln_w, *ln_b, *gamma; VConv pw1, pw2; int C; };
+struct VResUnit { VSnake a1, a2; VConv c1, c2; int dil; };
+struct VBlock { VSnake s; VConv up; int rate; VResUnit ru[3]; };
+struct VUpsample { VConv tconv; int ratio; VConvNext cn; };
+struct VocoderW {
+  const float* first_cb = nullptr;   // [size][vq]
+  const float* rest_cb = nullptr;    // [nq-1][size][vq]
+  VConv first_proj, rest_proj, pre_conv, in_proj, out_proj, init_conv, final_conv;
+  std::vector<VLayer> layers;
+  const float* final_norm = nullptr;
+  std::vector<VUpsample> ups;
+  std::vector<VBlock> blocks;
+  VSnake final_snake;
+};
+
+struct VocoderWorkspace {
+  DBuf codes, e_first, e_rest, a, b, c, d, qh, kh, vh;
+};
+
+struct q3_model {
+  q3_model_desc d;
+  int num_sms = 148;
+  bool finalized = false;
+  std::map<std::string, RawTensor> t;
+  std::vector<DBuf> owned;               // re-packed buffers
+  // talker
+  const bf16 *text_emb = nullptr, *codec_emb = nullptr, *fc1_w = nullptr, *fc1_b = nullptr, *fc2_w = nullptr,
+             *fc2_b = nullptr, *t_norm = nullptr, *codec_head = nullptr;
+  std::vector<LayerW> tl;
+  // code predictor
+  const bf16 *cp_proj_w = nullptr, *cp_proj_b = nullptr, *cp_norm = nullptr;
+  const bf16* cp_emb[15] = {nullptr};
+  const bf16* cp_head[15] = {nullptr};
+  std::vector<LayerW> cl;
+  const bf16 *cp_cos = nullptr, *cp_sin = nullptr;   // [cp_rope_positions][64]
+  bool has_talker = false, has_vocoder = false;
+  VocoderW voc;
+  mutable std::mutex voc_mutex;          // guards voc_ws for the session-less q3_vocoder_decode
+  mutable VocoderWorkspace voc_ws;
+  StackDims tdims() const { return {d.hidden, d.inter, d.heads, d.kv_heads, d.layers}; }
+  StackDims cdims() const { return {d.cp_hidden, d.cp_inter, d.cp_heads, d.cp_kv_heads, d.cp_layers}; }
+};
+
+void vocoder_finalize(q3_model* m);
+// codes: device i64 [B][nq][T]; pcm: device f32 [B][T*upsample]
+void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes, int B, int T, float* pcm,
+                 cudaStream_t st);
+int vocoder_total_upsample(const q3_model* m);
+// u32 frame-major codes [B][frames_cap][16] -> i64 [B][16][T] starting at frame f0 (codes_to_tensor, lib.rs:1417-1431)
+void vocoder_codes_to_tensor(const uint32_t* frames, int frames_cap, int f0, int T, int B, long long* out, cudaStream_t st);

@@ -1,0 +1,1052 @@
+// libq3tts_b200: model / session management, the decode loop and the C ABI (include/q3tts.h).
+// ref: src/lib.rs (generate_codes 530-656, StreamingSession 1484-1782), src/models/talker.rs,
+// src/models/code_predictor.rs, src/generation/sampling.rs.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "decode_kernels.cuh"
+#include "gemv.cuh"
+#include "model.h"
+
+std::atomic<uint64_t> g_q3_launches{0};
+static thread_local std::string g_last_error;
+
+// =================================================================================================
+// session object
+struct Scratch {
+  DBuf x, qkv, q, attn, o, normed, h1, act, tmp_e, tmp_p;
+  int tcap = 0;
+};
+
+struct q3_session {
+  const q3_model* m = nullptr;
+  int B = 0, max_seq = 0, frames_cap = 0;
+  q3_gen_config cfg{};
+  cudaStream_t st = nullptr;
+  // caches
+  DBuf tk_k, tk_v, cp_k, cp_v, cos_tab, sin_tab;
+  // per-row state (device)
+  DBuf cur_tok, done, n_frames, token_count, offset, frame_idx, rng, seen, last_hidden, trailing, lt, tts_pad, codes,
+      amax, frame_codes, logits, step_input, cp_x0, cp_xe, cp_logits, lens_dev;
+  int* host_flags = nullptr;       // mapped pinned
+  int* host_flags_dev = nullptr;
+  int lt_max = 1;
+  Scratch sc;
+  FrameState fs{};
+  // host mirrors
+  std::vector<int> prefill_len;
+  int frames_run = 0;              // loop iterations executed since prefill
+  bool prefilled = false, first_sampled = false;
+  // frame graph
+  cudaGraphExec_t graph_exec = nullptr;
+  bool graph_ok = false;
+  uint64_t graph_launches = 0;     // kernels inside one replay of the frame graph
+  // streaming
+  std::vector<int> stream_emitted;
+  VocoderWorkspace voc_ws;
+  DBuf voc_codes, voc_pcm;
+  // timing
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
+  q3_timing timing{};
+  ~q3_session() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (auto& e : ev_poll) if (e) cudaEventDestroy(e);
+    if (host_flags) cudaFreeHost(host_flags);
+    if (st) cudaStreamDestroy(st);
+  }
+};
+
+// =================================================================================================
+// helpers
+static const RawTensor& need_bf16(const q3_model* m, const std::string& name) {
+  auto it = m->t.find(name);
+  if (it == m->t.end()) throw Q3Error(Q3_ERR_MISSING_WEIGHT, "Missing weight: " + name);
+  if (it->second.dtype != Q3_BF16) throw Q3Error(Q3_ERR_INVALID, "talker weight must be stored bf16: " + name);
+  return it->second;
+}
+static const bf16* needb(const q3_model* m, const std::string& name) { return need_bf16(m, name).buf.as<bf16>(); }
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = f2bf(in[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = bf2f(in[i]);
+}
+__global__ void add_int_kernel(int* p, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += v;
+}
+
+// The frame graph bakes in buffer addresses and FrameState scalars; drop it when any of them changes.
+static void invalidate_graph(q3_session* s) {
+  if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+  s->graph_exec = nullptr;
+  s->graph_ok = false;
+}
+
+static void ensure_scratch(q3_session* s, int T) {
+  Scratch& sc = s->sc;
+  if (T <= sc.tcap) return;
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  invalidate_graph(s);
+  const q3_model_desc& d = s->m->d;
+  const int H = std::max(d.hidden, d.cp_hidden), I = std::max(d.inter, d.cp_inter);
+  const int nh = std::max(d.heads + 2 * d.kv_heads, d.cp_heads + 2 * d.cp_kv_heads);
+  const int qd = std::max(d.heads, d.cp_heads) * 128;
+  const int E = std::max(d.text_embed_dim, H);
+  sc.x.alloc((size_t)T * H * 2);
+  sc.qkv.alloc((size_t)T * nh * 128 * 2);
+  sc.q.alloc((size_t)T * qd * 2);
+  sc.attn.alloc((size_t)T * qd * 2);
+  sc.o.alloc((size_t)T * H * 2);
+  sc.normed.alloc((size_t)T * H * 2);
+  sc.h1.alloc((size_t)T * H * 2);
+  sc.act.alloc((size_t)T * I * 2);
+  sc.tmp_e.alloc((size_t)T * E * 2);
+  sc.tmp_p.alloc((size_t)T * E * 2);
+  sc.tcap = T;
+}
+
+// One decoder stack (talker or code predictor) over T = B*S tokens, in place on x.
+// ref: DecoderLayer::forward (transformer.rs:442-467) x layers.
+static void layers_forward(q3_session* s, const std::vector<LayerW>& L, const StackDims& dm, bf16* x, int T, int S,
+                           const int* pos_base, int pos_add, bf16* kc, bf16* vc, int cache_seq, const bf16* cos_tab,
+                           const bf16* sin_tab) {
+  const q3_model* m = s->m;
+  Scratch& sc = s->sc;
+  const int nh = dm.heads + 2 * dm.kv_heads;
+  const float eps = m->d.rms_eps;
+  const size_t layer_stride = (size_t)s->B * dm.kv_heads * cache_seq * 128;
+  for (int l = 0; l < dm.layers; ++l) {
+    const LayerW& w = L[l];
+    GemvArgs g{};
+    g.W = w.wqkv; g.X = x; g.ldx = dm.H; g.norm_w = w.in_ln; g.eps = eps; g.N = nh * 128; g.K = dm.H; g.T = T;
+    g.pro = PRO_RMSNORM; g.epi = EPI_STORE; g.Y = sc.qkv.as<bf16>(); g.ldy = nh * 128;
+    gemv_launch(g, m->num_sms, s->st);
+
+    RopeArgs r{};
+    r.qkv = sc.qkv.as<bf16>(); r.q_out = sc.q.as<bf16>();
+    r.k_cache = kc + l * layer_stride; r.v_cache = vc + l * layer_stride;
+    r.q_norm_w = w.q_norm; r.k_norm_w = w.k_norm; r.cos_tab = cos_tab; r.sin_tab = sin_tab;
+    r.pos_base = pos_base; r.pos_add = pos_add; r.S = S; r.T = T; r.heads = dm.heads; r.kv_heads = dm.kv_heads;
+    r.max_seq = cache_seq; r.eps = eps;
+    qk_norm_rope_append_kernel<<<dim3(ceil_div(nh, 4), T), 128, 0, s->st>>>(r);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+
+    AttnArgs a{};
+    a.q = sc.q.as<bf16>(); a.k_cache = r.k_cache; a.v_cache = r.v_cache; a.out = sc.attn.as<bf16>();
+    a.pos_base = pos_base; a.pos_add = pos_add; a.S = S; a.T = T; a.heads = dm.heads; a.kv_heads = dm.kv_heads;
+    a.max_seq = cache_seq;
+    attn_decode_kernel<<<dim3(dm.kv_heads, T), 256, attn_smem_bytes(cache_seq), s->st>>>(a);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+
+    GemvArgs o{};
+    o.W = w.wo; o.X = sc.attn.as<bf16>(); o.ldx = dm.heads * 128; o.N = dm.H; o.K = dm.heads * 128; o.T = T;
+    o.pro = PRO_NONE; o.epi = EPI_STORE; o.Y = sc.o.as<bf16>(); o.ldy = dm.H;
+    gemv_launch(o, m->num_sms, s->st);
+
+    fused_residual_rmsnorm_launch<bf16>(sc.o.as<bf16>(), x, w.post_ln, sc.normed.as<bf16>(), sc.h1.as<bf16>(), T, dm.H,
+                                        eps, s->st);
+
+    GemvArgs gu{};
+    gu.W = w.gate; gu.W2 = w.up; gu.X = sc.normed.as<bf16>(); gu.ldx = dm.H; gu.N = dm.I; gu.K = dm.H; gu.T = T;
+    gu.pro = PRO_NONE; gu.epi = EPI_SWIGLU; gu.Y = sc.act.as<bf16>(); gu.ldy = dm.I;
+    gemv_launch(gu, m->num_sms, s->st);
+
+    GemvArgs dn{};
+    dn.W = w.down; dn.X = sc.act.as<bf16>(); dn.ldx = dm.I; dn.N = dm.H; dn.K = dm.I; dn.T = T;
+    dn.pro = PRO_NONE; dn.epi = EPI_RESIDUAL; dn.R = sc.h1.as<bf16>(); dn.ldr = dm.H; dn.Y = x; dn.ldy = dm.H;
+    gemv_launch(dn, m->num_sms, s->st);
+  }
+}
+
+// text_proj(text_embedding[ids]) for n ids (device int array) -> out [n][hidden]   (talker.rs:294-321)
+static void text_project(q3_session* s, const int* ids_dev, int n, bf16* out) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  ensure_scratch(s, n);
+  gather_rows_kernel<<<n, 128, 0, s->st>>>(m->text_emb, ids_dev, d.text_embed_dim, d.text_vocab, s->sc.tmp_e.as<bf16>());
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  GemvArgs a{};
+  a.W = m->fc1_w; a.bias = m->fc1_b; a.X = s->sc.tmp_e.as<bf16>(); a.ldx = d.text_embed_dim; a.N = d.text_embed_dim;
+  a.K = d.text_embed_dim; a.T = n; a.pro = PRO_NONE; a.epi = EPI_BIAS_SILU; a.Y = s->sc.tmp_p.as<bf16>(); a.ldy = d.text_embed_dim;
+  gemv_launch(a, m->num_sms, s->st);
+  GemvArgs b{};
+  b.W = m->fc2_w; b.bias = m->fc2_b; b.X = s->sc.tmp_p.as<bf16>(); b.ldx = d.text_embed_dim; b.N = d.hidden;
+  b.K = d.text_embed_dim; b.T = n; b.pro = PRO_NONE; b.epi = EPI_BIAS; b.Y = out; b.ldy = d.hidden;
+  gemv_launch(b, m->num_sms, s->st);
+}
+
+static SampleArgs make_sample_args(const q3_gen_config& c, int V, int B) {
+  SampleArgs a{};
+  a.V = V; a.B = B;
+  a.use_temp = (c.temperature != 1.0 && c.temperature > 0.0) ? 1 : 0;      // sampling.rs:148
+  a.inv_temp = (float)(1.0 / c.temperature);
+  a.greedy = c.temperature < 0.01 ? 1 : 0;                                 // sampling.rs:155
+  a.top_k = c.top_k;
+  a.use_top_p = (c.top_p < 1.0 && c.top_p > 0.0) ? 1 : 0;                  // sampling.rs:167
+  a.top_p = (float)c.top_p;
+  a.use_pen = (c.repetition_penalty != 1.0 && std::fabs(c.repetition_penalty - 1.0) >= 1e-9) ? 1 : 0;
+  a.pen = (float)c.repetition_penalty;
+  a.inv_pen = 1.0f / (float)c.repetition_penalty;                          // sampling.rs:389-390 (f32 divide)
+  a.eos = c.eos_token_id;
+  a.min_new_tokens = c.min_new_tokens;
+  return a;
+}
+
+static void launch_sampler(q3_session* s, int advance) {
+  SampleArgs a = make_sample_args(s->cfg, s->m->d.codec_vocab, s->B);
+  a.logits = s->logits.as<float>();
+  a.seen = s->fs.seen; a.rng = s->fs.rng; a.tok_out = s->fs.cur_tok; a.token_count = s->fs.token_count;
+  a.done = s->fs.done; a.offset = s->fs.offset; a.frame_idx = s->fs.frame_idx; a.host_flags = nullptr;
+  a.advance = advance;
+  sample_kernel<<<s->B, 1024, 0, s->st>>>(a);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+
+// talker final norm + codec head; writes last_hidden (post-norm) and f32 logits (talker.rs:730-733)
+static void talker_head(q3_session* s, const bf16* x, int ldx) {
+  const q3_model* m = s->m;
+  GemvArgs h{};
+  h.W = m->codec_head; h.X = x; h.ldx = ldx; h.norm_w = m->t_norm; h.eps = m->d.rms_eps; h.xn_out = s->fs.last_hidden;
+  h.N = m->d.codec_vocab; h.K = m->d.hidden; h.T = s->B; h.pro = PRO_RMSNORM; h.epi = EPI_LOGITS; h.Yf = s->logits.as<float>();
+  gemv_launch(h, m->num_sms, s->st);
+}
+
+// The code-predictor part of one frame (code_predictor.rs:320-416): 15 dependent passes.
+static void cp_frame(q3_session* s, float* logits_out /* [15][B][cp_vocab] or null */) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  const int B = s->B, n_ac = d.groups - 1, H = d.hidden, C = d.cp_hidden;
+  ensure_scratch(s, 2 * B);
+  cp_begin_kernel<<<B, 256, 0, s->st>>>(s->fs, m->codec_emb, s->cp_x0.as<bf16>(), H, B, n_ac);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  bf16* x = s->sc.x.as<bf16>();
+  auto project = [&](const bf16* src, int T) {
+    if (m->cp_proj_w) {
+      GemvArgs p{};
+      p.W = m->cp_proj_w; p.bias = m->cp_proj_b; p.X = src; p.ldx = H; p.N = C; p.K = H; p.T = T;
+      p.pro = PRO_NONE; p.epi = EPI_BIAS; p.Y = x; p.ldy = C;
+      gemv_launch(p, m->num_sms, s->st);
+    } else {
+      Q3_CHECK_CUDA(cudaMemcpyAsync(x, src, (size_t)T * C * 2, cudaMemcpyDeviceToDevice, s->st));
+    }
+  };
+  auto head = [&](int g, const bf16* xin, int ldx) {
+    GemvArgs h{};
+    h.W = m->cp_head[g]; h.X = xin; h.ldx = ldx; h.norm_w = m->cp_norm; h.eps = d.rms_eps; h.N = d.cp_vocab; h.K = C;
+    h.T = B; h.pro = PRO_RMSNORM; h.epi = EPI_LOGITS; h.amax = s->fs.amax + (size_t)g * B;
+    h.Yf = logits_out ? logits_out + (size_t)g * B * d.cp_vocab : nullptr;
+    gemv_launch(h, m->num_sms, s->st);
+  };
+  // pass 0: two positions per row [talker_hidden, semantic_embed], causal, offset 0
+  project(s->cp_x0.as<bf16>(), 2 * B);
+  layers_forward(s, m->cl, m->cdims(), x, 2 * B, 2, nullptr, 0, s->cp_k.as<bf16>(), s->cp_v.as<bf16>(), d.cp_max_seq,
+                 m->cp_cos, m->cp_sin);
+  head(0, x + C, 2 * C);                      // logits from position 1 of every row
+  for (int g = 1; g < n_ac; ++g) {
+    cp_embed_kernel<<<B, 256, 0, s->st>>>(s->fs, m->cp_emb[g - 1], s->cp_xe.as<bf16>(), H, B, g);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    project(s->cp_xe.as<bf16>(), B);
+    layers_forward(s, m->cl, m->cdims(), x, B, 1, nullptr, g + 1, s->cp_k.as<bf16>(), s->cp_v.as<bf16>(), d.cp_max_seq,
+                   m->cp_cos, m->cp_sin);
+    head(g, x, C);
+  }
+}
+
+// everything of one loop iteration of generate_codes (lib.rs:580-652)
+static void frame_body(q3_session* s) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  cp_frame(s, nullptr);
+  EmbTable tab{};
+  for (int i = 0; i < d.groups - 1; ++i) tab.e[i] = m->cp_emb[i];
+  frame_finish_kernel<<<s->B, 256, 0, s->st>>>(s->fs, tab, m->codec_emb, s->step_input.as<bf16>(), d.hidden, s->B,
+                                               d.groups - 1);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  bf16* x = s->sc.x.as<bf16>();
+  Q3_CHECK_CUDA(cudaMemcpyAsync(x, s->step_input.p, (size_t)s->B * d.hidden * 2, cudaMemcpyDeviceToDevice, s->st));
+  layers_forward(s, m->tl, m->tdims(), x, s->B, 1, s->fs.offset, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq,
+                 s->cos_tab.as<bf16>(), s->sin_tab.as<bf16>());
+  talker_head(s, x, d.hidden);
+  launch_sampler(s, 1);
+}
+
+static void run_frames(q3_session* s, int n) {
+  if (n <= 0) return;
+  // KV overflow check (kv_cache.rs:293-300)
+  int max_len = 0;
+  for (int b = 0; b < s->B; ++b) max_len = std::max(max_len, s->prefill_len[b]);
+  if (max_len + s->frames_run + n > s->max_seq)
+    throw Q3Error(Q3_ERR_KV_OVERFLOW, "KV cache overflow: current=" + std::to_string(max_len + s->frames_run) +
+                                          " + new=" + std::to_string(n) + " > max=" + std::to_string(s->max_seq));
+  int done_frames = 0;
+  uint64_t per_frame = 0;
+  if (!s->graph_ok) {
+    // first frame eagerly (also performs every lazy cudaFuncSetAttribute), then capture one frame
+    uint64_t before = g_q3_launches.load();
+    frame_body(s);
+    per_frame = g_q3_launches.load() - before;
+    done_frames = 1;
+    if (n > 1) {
+      cudaGraph_t graph = nullptr;
+      Q3_CHECK_CUDA(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+      try {
+        frame_body(s);
+      } catch (...) {
+        cudaStreamEndCapture(s->st, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+      }
+      Q3_CHECK_CUDA(cudaStreamEndCapture(s->st, &graph));
+      g_q3_launches.fetch_sub(per_frame);      // the captured launches did not execute
+      Q3_CHECK_CUDA(cudaGraphInstantiate(&s->graph_exec, graph, 0));
+      cudaGraphDestroy(graph);
+      s->graph_ok = true;
+      s->graph_launches = per_frame;
+    }
+  }
+  const uint64_t graph_launches = s->graph_launches;
+  const int poll_every = 16;
+  int blk = 0;
+  bool stop = false;
+  while (done_frames < n && !stop) {
+    int todo = std::min(poll_every, n - done_frames);
+    for (int i = 0; i < todo; ++i) {
+      Q3_CHECK_CUDA(cudaGraphLaunch(s->graph_exec, s->st));
+      g_q3_launches.fetch_add(graph_launches);
+    }
+    done_frames += todo;
+    count_active_kernel<<<1, 32, 0, s->st>>>(s->fs.done, s->B, s->host_flags_dev + (blk & 1));
+    Q3_COUNT_LAUNCH();
+    Q3_CHECK_CUDA(cudaEventRecord(s->ev_poll[blk & 1], s->st));
+    if (blk > 0) {
+      // look at the flag written one block ago: no pipeline drain
+      Q3_CHECK_CUDA(cudaEventSynchronize(s->ev_poll[(blk - 1) & 1]));
+      if (s->host_flags[(blk - 1) & 1] == 0) stop = true;
+    }
+    ++blk;
+  }
+  s->frames_run += done_frames;
+}
+
+static void sample_first_if_needed(q3_session* s) {
+  if (s->first_sampled) return;
+  launch_sampler(s, 0);                       // lib.rs:557-571, token_count = 0
+  s->first_sampled = true;
+}
+
+// =================================================================================================
+// ABI
+#define Q3_API_BEGIN try {
+#define Q3_API_END                                                       \
+  }                                                                      \
+  catch (const Q3Error& e) { g_last_error = e.what(); return e.code; }   \
+  catch (const std::exception& e) { g_last_error = e.what(); return Q3_ERR_INVALID; } \
+  catch (...) { g_last_error = "unknown error"; return Q3_ERR_INVALID; } \
+  return Q3_OK;
+
+extern "C" {
+
+const char* q3_last_error(void) { return g_last_error.c_str(); }
+int q3_abi_version(void) { return Q3_ABI_VERSION; }
+uint64_t q3_kernel_launch_count(void) { return g_q3_launches.load(); }
+
+q3_status q3_model_create(const q3_model_desc* desc, q3_model** out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(desc && out, Q3_ERR_INVALID, "null argument");
+  int ndev = 0;
+  Q3_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+  Q3_REQUIRE(ndev > 0 && desc->device < ndev, Q3_ERR_CUDA, "no usable CUDA device (there is no CPU fallback)");
+  cudaDeviceProp prop;
+  Q3_CHECK_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+  Q3_REQUIRE(prop.major == 10, Q3_ERR_CUDA, "libq3tts_b200 is built for sm_100a only; found sm_" +
+                                                std::to_string(prop.major) + std::to_string(prop.minor));
+  Q3_REQUIRE(desc->head_dim == 128, Q3_ERR_UNSUPPORTED, "head_dim must be 128");
+  Q3_REQUIRE(desc->heads == 2 * desc->kv_heads && desc->cp_heads == 2 * desc->cp_kv_heads, Q3_ERR_UNSUPPORTED,
+             "GQA group size must be 2");
+  Q3_REQUIRE(desc->codec_vocab <= 4096 && desc->codec_vocab > 1024, Q3_ERR_UNSUPPORTED, "codec vocab must be in (1024, 4096]");
+  Q3_REQUIRE(desc->groups == 16, Q3_ERR_UNSUPPORTED, "16 code groups expected");
+  Q3_REQUIRE(desc->hidden % 8 == 0 && desc->cp_hidden % 8 == 0 && desc->inter % 8 == 0 && desc->cp_inter % 8 == 0 &&
+                 desc->text_embed_dim % 8 == 0,
+             Q3_ERR_UNSUPPORTED, "dimensions must be multiples of 8");
+  Q3_CHECK_CUDA(cudaSetDevice(desc->device));
+  auto* m = new q3_model();
+  m->d = *desc;
+  m->num_sms = prop.multiProcessorCount;
+  *out = m;
+  Q3_API_END
+}
+
+q3_status q3_model_set_tensor(q3_model* m, const char* hf_name, const void* data, q3_dtype dtype, const int64_t* shape,
+                              int32_t ndim, int32_t on_device) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(m && hf_name && data && shape && ndim > 0 && ndim <= 4, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(!m->finalized, Q3_ERR_STATE, "model already finalized");
+  Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
+  std::string name(hf_name);
+  RawTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const size_t n = t.numel();
+  const bool is_voc = name.rfind("decoder.", 0) == 0;
+  const q3_dtype want = is_voc ? Q3_F32 : Q3_BF16;
+  const size_t src_bytes = n * (dtype == Q3_BF16 ? 2 : 4);
+  DBuf src;
+  const void* dsrc = data;
+  if (!on_device) {
+    src.alloc(src_bytes);
+    Q3_CHECK_CUDA(cudaMemcpy(src.p, data, src_bytes, cudaMemcpyHostToDevice));
+    dsrc = src.p;
+  }
+  t.dtype = want;
+  t.buf.alloc(n * (want == Q3_BF16 ? 2 : 4));
+  if (dtype == want) {
+    Q3_CHECK_CUDA(cudaMemcpy(t.buf.p, dsrc, src_bytes, cudaMemcpyDeviceToDevice));
+  } else if (want == Q3_BF16) {
+    f32_to_bf16_kernel<<<1024, 256>>>((const float*)dsrc, t.buf.as<bf16>(), n);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    Q3_CHECK_CUDA(cudaDeviceSynchronize());
+  } else {
+    bf16_to_f32_kernel<<<1024, 256>>>((const bf16*)dsrc, t.buf.as<float>(), n);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    Q3_CHECK_CUDA(cudaDeviceSynchronize());
+  }
+  m->t[name] = std::move(t);
+  Q3_API_END
+}
+
+static void check_shape(const RawTensor& t, std::initializer_list<int64_t> want, const std::string& name) {
+  std::vector<int64_t> w(want);
+  if (t.shape != w) {
+    std::string s = "shape mismatch for " + name + ": got [";
+    for (auto d : t.shape) s += std::to_string(d) + ",";
+    s += "] want [";
+    for (auto d : w) s += std::to_string(d) + ",";
+    throw Q3Error(Q3_ERR_INVALID, s + "]");
+  }
+}
+
+static void build_stack(q3_model* m, const std::string& prefix, const StackDims& dm, std::vector<LayerW>& out) {
+  out.clear();
+  const int qd = dm.heads * 128, kd = dm.kv_heads * 128;
+  for (int l = 0; l < dm.layers; ++l) {
+    const std::string p = prefix + ".layers." + std::to_string(l);
+    LayerW w{};
+    w.in_ln = needb(m, p + ".input_layernorm.weight");
+    w.post_ln = needb(m, p + ".post_attention_layernorm.weight");
+    w.q_norm = needb(m, p + ".self_attn.q_norm.weight");
+    w.k_norm = needb(m, p + ".self_attn.k_norm.weight");
+    const RawTensor& q = need_bf16(m, p + ".self_attn.q_proj.weight");
+    const RawTensor& k = need_bf16(m, p + ".self_attn.k_proj.weight");
+    const RawTensor& v = need_bf16(m, p + ".self_attn.v_proj.weight");
+    check_shape(q, {qd, dm.H}, p + ".q_proj");
+    check_shape(k, {kd, dm.H}, p + ".k_proj");
+    check_shape(v, {kd, dm.H}, p + ".v_proj");
+    // fused [q;k;v] weight so one pass over the activations yields all three projections
+    DBuf fused;
+    fused.alloc((size_t)(qd + 2 * kd) * dm.H * 2);
+    Q3_CHECK_CUDA(cudaMemcpy(fused.p, q.buf.p, (size_t)qd * dm.H * 2, cudaMemcpyDeviceToDevice));
+    Q3_CHECK_CUDA(cudaMemcpy((char*)fused.p + (size_t)qd * dm.H * 2, k.buf.p, (size_t)kd * dm.H * 2, cudaMemcpyDeviceToDevice));
+    Q3_CHECK_CUDA(cudaMemcpy((char*)fused.p + (size_t)(qd + kd) * dm.H * 2, v.buf.p, (size_t)kd * dm.H * 2, cudaMemcpyDeviceToDevice));
+    w.wqkv = fused.as<bf16>();
+    m->owned.push_back(std::move(fused));
+    m->t.erase(p + ".self_attn.q_proj.weight");
+    m->t.erase(p + ".self_attn.k_proj.weight");
+    m->t.erase(p + ".self_attn.v_proj.weight");
+    const RawTensor& o = need_bf16(m, p + ".self_attn.o_proj.weight");
+    check_shape(o, {dm.H, qd}, p + ".o_proj");
+    w.wo = o.buf.as<bf16>();
+    const RawTensor& g = need_bf16(m, p + ".mlp.gate_proj.weight");
+    const RawTensor& u = need_bf16(m, p + ".mlp.up_proj.weight");
+    const RawTensor& dn = need_bf16(m, p + ".mlp.down_proj.weight");
+    check_shape(g, {dm.I, dm.H}, p + ".gate_proj");
+    check_shape(u, {dm.I, dm.H}, p + ".up_proj");
+    check_shape(dn, {dm.H, dm.I}, p + ".down_proj");
+    w.gate = g.buf.as<bf16>(); w.up = u.buf.as<bf16>(); w.down = dn.buf.as<bf16>();
+    out.push_back(w);
+  }
+}
+
+// bf16 RoPE tables: angle = (float)pos * inv_freq (f32), cos/sin in f32, then rounded to the activation
+// dtype before use (transformer.rs:48-57, 79-90, 133-175).
+static void build_rope_table(int n_pos, float theta, DBuf& cos_out, DBuf& sin_out) {
+  std::vector<uint16_t> c((size_t)n_pos * 64), s((size_t)n_pos * 64);
+  float inv[64];
+  for (int i = 0; i < 64; ++i) inv[i] = 1.0f / powf(theta, (float)(2 * i) / 128.0f);
+  auto to_bf16 = [](float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    uint32_t r = u + 0x7fffu + ((u >> 16) & 1u);       // round to nearest even (finite inputs)
+    return (uint16_t)(r >> 16);
+  };
+  for (int p = 0; p < n_pos; ++p)
+    for (int i = 0; i < 64; ++i) {
+      float ang = (float)p * inv[i];
+      c[(size_t)p * 64 + i] = to_bf16(cosf(ang));
+      s[(size_t)p * 64 + i] = to_bf16(sinf(ang));
+    }
+  cos_out.alloc(c.size() * 2);
+  sin_out.alloc(s.size() * 2);
+  Q3_CHECK_CUDA(cudaMemcpy(cos_out.p, c.data(), c.size() * 2, cudaMemcpyHostToDevice));
+  Q3_CHECK_CUDA(cudaMemcpy(sin_out.p, s.data(), s.size() * 2, cudaMemcpyHostToDevice));
+}
+
+q3_status q3_model_finalize(q3_model* m) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(m, Q3_ERR_INVALID, "null model");
+  Q3_REQUIRE(!m->finalized, Q3_ERR_STATE, "model already finalized");
+  Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
+  const q3_model_desc& d = m->d;
+  const bool any_talker = m->t.count("talker.model.norm.weight") > 0;
+  const bool any_voc = m->t.count("decoder.pre_conv.conv.weight") > 0;
+  Q3_REQUIRE(any_talker || any_voc, Q3_ERR_MISSING_WEIGHT, "Missing weight: no talker.* or decoder.* tensors were set");
+  if (any_talker) {
+    m->codec_emb = needb(m, "talker.model.codec_embedding.weight");
+    check_shape(need_bf16(m, "talker.model.codec_embedding.weight"), {d.codec_vocab, d.hidden}, "codec_embedding");
+    if (m->t.count("talker.model.text_embedding.weight")) {
+      m->text_emb = needb(m, "talker.model.text_embedding.weight");
+      m->fc1_w = needb(m, "talker.text_projection.linear_fc1.weight");
+      m->fc1_b = needb(m, "talker.text_projection.linear_fc1.bias");
+      m->fc2_w = needb(m, "talker.text_projection.linear_fc2.weight");
+      m->fc2_b = needb(m, "talker.text_projection.linear_fc2.bias");
+    }
+    build_stack(m, "talker.model", m->tdims(), m->tl);
+    m->t_norm = needb(m, "talker.model.norm.weight");
+    m->codec_head = needb(m, "talker.codec_head.weight");
+    check_shape(need_bf16(m, "talker.codec_head.weight"), {d.codec_vocab, d.hidden}, "codec_head");
+    const std::string cp = "talker.code_predictor";
+    if (d.hidden != d.cp_hidden) {
+      m->cp_proj_w = needb(m, cp + ".small_to_mtp_projection.weight");
+      m->cp_proj_b = needb(m, cp + ".small_to_mtp_projection.bias");
+      check_shape(need_bf16(m, cp + ".small_to_mtp_projection.weight"), {d.cp_hidden, d.hidden}, "small_to_mtp_projection");
+    }
+    for (int g = 0; g < d.groups - 1; ++g) {
+      m->cp_emb[g] = needb(m, cp + ".model.codec_embedding." + std::to_string(g) + ".weight");
+      m->cp_head[g] = needb(m, cp + ".lm_head." + std::to_string(g) + ".weight");
+      check_shape(need_bf16(m, cp + ".model.codec_embedding." + std::to_string(g) + ".weight"), {d.cp_vocab, d.hidden}, "cp codec_embedding");
+      check_shape(need_bf16(m, cp + ".lm_head." + std::to_string(g) + ".weight"), {d.cp_vocab, d.cp_hidden}, "lm_head");
+    }
+    build_stack(m, cp + ".model", m->cdims(), m->cl);
+    m->cp_norm = needb(m, cp + ".model.norm.weight");
+    DBuf c, s;
+    build_rope_table(d.cp_rope_positions, d.rope_theta, c, s);
+    m->cp_cos = c.as<bf16>();
+    m->cp_sin = s.as<bf16>();
+    m->owned.push_back(std::move(c));
+    m->owned.push_back(std::move(s));
+    m->has_talker = true;
+  }
+  if (any_voc) vocoder_finalize(m);
+  Q3_CHECK_CUDA(cudaDeviceSynchronize());
+  m->finalized = true;
+  Q3_API_END
+}
+
+void q3_model_destroy(q3_model* m) { delete m; }
+
+// -------------------------------------------------------------------------------------------------
+static void reset_state(q3_session* s, const uint64_t* seeds) {
+  const int B = s->B;
+  std::vector<unsigned long long> st(B);
+  for (int b = 0; b < B; ++b)   // SamplingContext::new (sampling.rs:36-38)
+    st[b] = (unsigned long long)seeds[b] * 2685821657736338717ull + 1442695040888963407ull;
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->rng.p, st.data(), B * 8, cudaMemcpyHostToDevice, s->st));
+  s->cur_tok.zero(s->st); s->done.zero(s->st); s->n_frames.zero(s->st); s->token_count.zero(s->st);
+  s->offset.zero(s->st); s->frame_idx.zero(s->st); s->seen.zero(s->st); s->amax.zero(s->st);
+  s->frame_codes.zero(s->st);
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  s->prefilled = false;
+  s->first_sampled = false;
+  s->frames_run = 0;
+  std::fill(s->prefill_len.begin(), s->prefill_len.end(), 0);
+  std::fill(s->stream_emitted.begin(), s->stream_emitted.end(), 0);
+}
+
+q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, const q3_gen_config* cfg,
+                            const uint64_t* seeds, q3_session** out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(m && cfg && seeds && out, Q3_ERR_INVALID, "null argument");
+  Q3_REQUIRE(m->finalized && m->has_talker, Q3_ERR_STATE, "model has no finalized talker weights");
+  Q3_REQUIRE(batch >= 1 && batch <= 256, Q3_ERR_INVALID, "batch must be in [1, 256]");
+  Q3_REQUIRE(max_seq >= 8 && max_seq <= 12288, Q3_ERR_INVALID, "max_seq must be in [8, 12288]");
+  Q3_REQUIRE(cfg->max_new_tokens >= 1, Q3_ERR_INVALID, "max_new_tokens must be >= 1");
+  Q3_REQUIRE(cfg->eos_token_id < m->d.codec_vocab, Q3_ERR_INVALID, "eos_token_id out of range");
+  Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
+  const q3_model_desc& d = m->d;
+  std::unique_ptr<q3_session> s(new q3_session());
+  s->m = m; s->B = batch; s->max_seq = max_seq; s->cfg = *cfg;
+  s->frames_cap = std::min(cfg->max_new_tokens, max_seq);
+  Q3_CHECK_CUDA(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+  Q3_CHECK_CUDA(cudaEventCreate(&s->ev0));
+  Q3_CHECK_CUDA(cudaEventCreate(&s->ev1));
+  for (auto& e : s->ev_poll) Q3_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  const int B = batch, V = d.codec_vocab, H = d.hidden;
+  s->tk_k.alloc((size_t)d.layers * B * d.kv_heads * max_seq * 128 * 2);
+  s->tk_v.alloc((size_t)d.layers * B * d.kv_heads * max_seq * 128 * 2);
+  s->cp_k.alloc((size_t)d.cp_layers * B * d.cp_kv_heads * d.cp_max_seq * 128 * 2);
+  s->cp_v.alloc((size_t)d.cp_layers * B * d.cp_kv_heads * d.cp_max_seq * 128 * 2);
+  s->tk_k.zero(); s->tk_v.zero(); s->cp_k.zero(); s->cp_v.zero();       // PreAllocKVCache::new zero-fills
+  build_rope_table(max_seq, d.rope_theta, s->cos_tab, s->sin_tab);
+  s->cur_tok.alloc(B * 4); s->done.alloc(B * 4); s->n_frames.alloc(B * 4); s->token_count.alloc(B * 4);
+  s->offset.alloc(B * 4); s->frame_idx.alloc(B * 4); s->rng.alloc(B * 8); s->seen.alloc((size_t)B * V);
+  s->last_hidden.alloc((size_t)B * H * 2); s->tts_pad.alloc((size_t)H * 2); s->lt.alloc(B * 4);
+  s->trailing.alloc((size_t)B * H * 2);
+  s->codes.alloc((size_t)B * s->frames_cap * 16 * 4);
+  s->amax.alloc((size_t)15 * B * 8); s->frame_codes.alloc((size_t)B * 16 * 4);
+  s->logits.alloc((size_t)B * V * 4); s->step_input.alloc((size_t)B * H * 2);
+  s->cp_x0.alloc((size_t)2 * B * H * 2); s->cp_xe.alloc((size_t)B * H * 2);
+  s->lens_dev.alloc(B * 4);
+  s->tts_pad.zero(); s->lt.zero(); s->trailing.zero(); s->codes.zero(); s->last_hidden.zero();
+  Q3_CHECK_CUDA(cudaHostAlloc((void**)&s->host_flags, 64, cudaHostAllocMapped));
+  s->host_flags[0] = s->host_flags[1] = B;
+  Q3_CHECK_CUDA(cudaHostGetDevicePointer((void**)&s->host_flags_dev, s->host_flags, 0));
+  s->prefill_len.assign(B, 0);
+  s->stream_emitted.assign(B, 0);
+  ensure_scratch(s.get(), 2 * B);
+  if (attn_smem_bytes(max_seq) > 48 * 1024)
+    Q3_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)attn_smem_bytes(max_seq)));
+  FrameState& fs = s->fs;
+  fs.cur_tok = s->cur_tok.as<uint32_t>(); fs.done = s->done.as<int>(); fs.n_frames = s->n_frames.as<int>();
+  fs.token_count = s->token_count.as<int>(); fs.offset = s->offset.as<int>(); fs.frame_idx = s->frame_idx.as<int>();
+  fs.rng = s->rng.as<unsigned long long>(); fs.seen = s->seen.as<uint8_t>(); fs.last_hidden = s->last_hidden.as<bf16>();
+  fs.trailing = s->trailing.as<bf16>(); fs.lt = s->lt.as<int>(); fs.lt_max = 1; fs.tts_pad = s->tts_pad.as<bf16>();
+  fs.codes = s->codes.as<uint32_t>(); fs.frames_cap = s->frames_cap; fs.amax = s->amax.as<unsigned long long>();
+  fs.frame_codes = s->frame_codes.as<uint32_t>(); fs.host_flags = s->host_flags_dev;
+  reset_state(s.get(), seeds);
+  *out = s.release();
+  Q3_API_END
+}
+
+q3_status q3_session_reset(q3_session* s, const uint64_t* seeds) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && seeds, Q3_ERR_INVALID, "null argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  reset_state(s, seeds);
+  Q3_API_END
+}
+
+void q3_session_destroy(q3_session* s) {
+  if (!s) return;
+  cudaSetDevice(s->m->d.device);
+  if (s->st) cudaStreamSynchronize(s->st);
+  delete s;
+}
+
+void* q3_session_stream(q3_session* s) { return s ? (void*)s->st : nullptr; }
+
+q3_status q3_session_synchronize(q3_session* s) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s, Q3_ERR_INVALID, "null session");
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  Q3_API_END
+}
+
+// prefill over device-resident embeddings x [B][l_max][H] (in scratch x)
+static void prefill_run(q3_session* s, const int32_t* lens, int l_max) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  const int B = s->B, T = B * l_max;
+  for (int b = 0; b < B; ++b) {
+    Q3_REQUIRE(lens[b] >= 1 && lens[b] <= l_max, Q3_ERR_INVALID, "prefill length out of range");
+    if (lens[b] > s->max_seq)
+      throw Q3Error(Q3_ERR_KV_OVERFLOW, "KV cache overflow: current=0 + new=" + std::to_string(lens[b]) + " > max=" +
+                                            std::to_string(s->max_seq));
+  }
+  Q3_REQUIRE(l_max <= s->max_seq, Q3_ERR_KV_OVERFLOW, "KV cache overflow: padded prefill exceeds max_seq");
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
+  bf16* x = s->sc.x.as<bf16>();
+  layers_forward(s, m->tl, m->tdims(), x, T, l_max, nullptr, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq,
+                 s->cos_tab.as<bf16>(), s->sin_tab.as<bf16>());
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->lens_dev.p, lens, B * 4, cudaMemcpyHostToDevice, s->st));
+  gather_last_kernel<<<B, 128, 0, s->st>>>(x, s->lens_dev.as<int>(), l_max, d.hidden, s->sc.o.as<bf16>());
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  talker_head(s, s->sc.o.as<bf16>(), d.hidden);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->offset.p, lens, B * 4, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  Q3_CHECK_CUDA(cudaEventElapsedTime(&s->timing.prefill_ms, s->ev0, s->ev1));
+  for (int b = 0; b < B; ++b) s->prefill_len[b] = lens[b];
+  s->prefilled = true;
+  s->first_sampled = false;
+  s->frames_run = 0;
+}
+
+q3_status q3_prefill_embeds(q3_session* s, const uint16_t* embeds, const int32_t* lens, int32_t l_max) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && embeds && lens && l_max >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(!s->prefilled, Q3_ERR_STATE, "session already prefilled; call q3_session_reset first");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  ensure_scratch(s, s->B * l_max);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->sc.x.p, embeds, (size_t)s->B * l_max * s->m->d.hidden * 2, cudaMemcpyHostToDevice, s->st));
+  prefill_run(s, lens, l_max);
+  Q3_API_END
+}
+
+q3_status q3_prefill_ids(q3_session* s, const int32_t* text_ids, const int32_t* codec_ids, const int32_t* lens, int32_t l_max) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && text_ids && codec_ids && lens && l_max >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(!s->prefilled, Q3_ERR_STATE, "session already prefilled; call q3_session_reset first");
+  Q3_REQUIRE(s->m->text_emb, Q3_ERR_MISSING_WEIGHT, "Missing weight: talker.model.text_embedding.weight");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  const int T = s->B * l_max;
+  for (int i = 0; i < T; ++i) {
+    Q3_REQUIRE(text_ids[i] < d.text_vocab && codec_ids[i] < d.codec_vocab, Q3_ERR_INVALID, "token id out of range");
+  }
+  ensure_scratch(s, T);
+  DBuf tid, cid;
+  tid.alloc(T * 4); cid.alloc(T * 4);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(tid.p, text_ids, T * 4, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(cid.p, codec_ids, T * 4, cudaMemcpyHostToDevice, s->st));
+  text_project(s, tid.as<int>(), T, s->sc.o.as<bf16>());
+  assemble_embeds_kernel<<<T, 256, 0, s->st>>>(s->sc.o.as<bf16>(), tid.as<int>(), cid.as<int>(), s->m->codec_emb, d.hidden,
+                                               s->sc.x.as<bf16>());
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  prefill_run(s, lens, l_max);
+  Q3_API_END
+}
+
+q3_status q3_set_trailing_text(q3_session* s, const uint16_t* trailing, const int32_t* lt, int32_t lt_max, const uint16_t* tts_pad) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && trailing && lt && tts_pad && lt_max >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const int H = s->m->d.hidden;
+  for (int b = 0; b < s->B; ++b) Q3_REQUIRE(lt[b] >= 0 && lt[b] <= lt_max, Q3_ERR_INVALID, "trailing length out of range");
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  if (lt_max != s->lt_max || (size_t)s->B * lt_max * H * 2 > s->trailing.bytes) invalidate_graph(s);
+  s->trailing.ensure((size_t)s->B * lt_max * H * 2);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->trailing.p, trailing, (size_t)s->B * lt_max * H * 2, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->lt.p, lt, s->B * 4, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->tts_pad.p, tts_pad, (size_t)H * 2, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  s->lt_max = lt_max;
+  s->fs.trailing = s->trailing.as<bf16>();
+  s->fs.lt_max = lt_max;
+  Q3_API_END
+}
+
+q3_status q3_set_trailing_ids(q3_session* s, const int32_t* ids, const int32_t* n, int32_t n_max, int32_t tts_eos_id,
+                              int32_t tts_pad_id) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && n && n_max >= 0 && (ids || n_max == 0), Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(s->m->text_emb, Q3_ERR_MISSING_WEIGHT, "Missing weight: talker.model.text_embedding.weight");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  const int B = s->B, H = d.hidden, lt_max = n_max + 1;
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  if (lt_max != s->lt_max || (size_t)B * lt_max * H * 2 > s->trailing.bytes) invalidate_graph(s);
+  // rows: ids[b][0..n-1] ++ tts_eos (lib.rs:508-516); one extra row at the end for tts_pad
+  std::vector<int> all((size_t)B * lt_max + 1, tts_pad_id), lt(B);
+  for (int b = 0; b < B; ++b) {
+    Q3_REQUIRE(n[b] >= 0 && n[b] <= n_max, Q3_ERR_INVALID, "trailing length out of range");
+    for (int i = 0; i < n[b]; ++i) {
+      int id = ids[(size_t)b * n_max + i];
+      Q3_REQUIRE(id >= 0 && id < d.text_vocab, Q3_ERR_INVALID, "text id out of range");
+      all[(size_t)b * lt_max + i] = id;
+    }
+    all[(size_t)b * lt_max + n[b]] = tts_eos_id;
+    lt[b] = n[b] + 1;
+  }
+  const int T = B * lt_max + 1;
+  DBuf idd, proj;
+  idd.alloc(T * 4);
+  proj.alloc((size_t)T * H * 2);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(idd.p, all.data(), T * 4, cudaMemcpyHostToDevice, s->st));
+  text_project(s, idd.as<int>(), T, proj.as<bf16>());
+  s->trailing.ensure((size_t)B * lt_max * H * 2);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->trailing.p, proj.p, (size_t)B * lt_max * H * 2, cudaMemcpyDeviceToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->tts_pad.p, proj.as<bf16>() + (size_t)B * lt_max * H, (size_t)H * 2, cudaMemcpyDeviceToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->lt.p, lt.data(), B * 4, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  s->lt_max = lt_max;
+  s->fs.trailing = s->trailing.as<bf16>();
+  s->fs.lt_max = lt_max;
+  Q3_API_END
+}
+
+static int frames_budget(q3_session* s, int max_frames) {
+  // the reference loop runs `for frame_idx in 0..max_new_tokens` (lib.rs:580)
+  return std::max(0, std::min(max_frames, s->cfg.max_new_tokens - s->frames_run));
+}
+
+q3_status q3_generate_async(q3_session* s, int32_t max_frames) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && max_frames >= 0, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(s->prefilled, Q3_ERR_STATE, "q3_generate before prefill");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
+  sample_first_if_needed(s);
+  run_frames(s, frames_budget(s, max_frames));
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
+  Q3_API_END
+}
+
+q3_status q3_get_codes(q3_session* s, int32_t max_frames, uint32_t* codes, int32_t* n_frames) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && codes && n_frames && max_frames >= 0, Q3_ERR_INVALID, "bad argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const int B = s->B;
+  Q3_CHECK_CUDA(cudaMemcpyAsync(n_frames, s->n_frames.p, B * 4, cudaMemcpyDeviceToHost, s->st));
+  const int take = std::min(max_frames, s->frames_cap);
+  if (take > 0)
+    Q3_CHECK_CUDA(cudaMemcpy2DAsync(codes, (size_t)max_frames * 64, s->codes.p, (size_t)s->frames_cap * 64, (size_t)take * 64, B,
+                                    cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  for (int b = 0; b < B; ++b) n_frames[b] = std::min(n_frames[b], max_frames);
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->timing.generation_ms = ms;
+  int mx = 0;
+  for (int b = 0; b < B; ++b) mx = std::max(mx, n_frames[b]);
+  s->timing.generation_frames = mx;
+  Q3_API_END
+}
+
+q3_status q3_generate(q3_session* s, int32_t max_frames, uint32_t* codes, int32_t* n_frames) {
+  q3_status st = q3_generate_async(s, max_frames);
+  if (st != Q3_OK) return st;
+  return q3_get_codes(s, max_frames, codes, n_frames);
+}
+
+// vocode frames [f0, f0+T) of every row (rows shorter than that are padded with their own frame 0.. and zeroed after)
+static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& row_len, float* pcm_host, size_t pcm_row_stride) {
+  const q3_model* m = s->m;
+  const int B = s->B, up = vocoder_total_upsample(m);
+  if (T <= 0) return;
+  s->voc_codes.ensure((size_t)B * 16 * T * 8);
+  s->voc_pcm.ensure((size_t)B * T * up * 4);
+  // rows decode independently (the vocoder is causal per row), so one batched call over T frames and a
+  // per-row truncation reproduces B separate Decoder12Hz::decode calls of length row_len[b].
+  vocoder_codes_to_tensor(s->codes.as<uint32_t>(), s->frames_cap, f0, T, B, s->voc_codes.as<long long>(), s->st);
+  vocoder_run(m, s->voc_ws, s->voc_codes.as<long long>(), B, T, s->voc_pcm.as<float>(), s->st);
+  if (pcm_host) {
+    for (int b = 0; b < B; ++b) {
+      const size_t n = (size_t)row_len[b] * up;
+      if (n) Q3_CHECK_CUDA(cudaMemcpyAsync(pcm_host + b * pcm_row_stride, s->voc_pcm.as<float>() + (size_t)b * T * up, n * 4,
+                                           cudaMemcpyDeviceToHost, s->st));
+    }
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+    for (int b = 0; b < B; ++b) {
+      const size_t n = (size_t)row_len[b] * up;
+      if (n < (size_t)T * up) memset(pcm_host + b * pcm_row_stride + n, 0, ((size_t)T * up - n) * 4);
+    }
+  }
+}
+
+q3_status q3_vocode_session(q3_session* s, int32_t max_frames, float* pcm) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && max_frames >= 0, Q3_ERR_INVALID, "bad argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  std::vector<int> nf(s->B);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(nf.data(), s->n_frames.p, s->B * 4, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  int T = 0;
+  for (int b = 0; b < s->B; ++b) { nf[b] = std::min(nf[b], max_frames); T = std::max(T, nf[b]); }
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
+  const int up = vocoder_total_upsample(s->m);
+  if (pcm && T < max_frames)
+    for (int b = 0; b < s->B; ++b) memset(pcm + (size_t)b * max_frames * up, 0, (size_t)max_frames * up * 4);
+  vocode_rows(s, 0, T, nf, pcm, (size_t)max_frames * up);
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  Q3_CHECK_CUDA(cudaEventElapsedTime(&s->timing.decode_ms, s->ev0, s->ev1));
+  Q3_API_END
+}
+
+q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_frames, int32_t* done) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && codes && pcm && n_frames && done, Q3_ERR_INVALID, "null argument");
+  Q3_REQUIRE(s->prefilled, Q3_ERR_STATE, "q3_stream_next before prefill");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const int B = s->B, chunk = std::max(1, s->cfg.chunk_frames), up = vocoder_total_upsample(s->m);
+  sample_first_if_needed(s);
+  run_frames(s, frames_budget(s, chunk));
+  std::vector<int> nf(B), dn(B);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(nf.data(), s->n_frames.p, B * 4, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(dn.data(), s->done.p, B * 4, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  // every row emits the frames it produced since the last chunk; all rows share the same f0 only while
+  // none has finished, so decode per distinct start offset.
+  bool all_done = true;
+  std::vector<int> len(B);
+  int T = 0;
+  for (int b = 0; b < B; ++b) {
+    len[b] = std::min(nf[b] - s->stream_emitted[b], chunk);
+    n_frames[b] = len[b];
+    T = std::max(T, len[b]);
+    const bool row_done = dn[b] || nf[b] >= s->cfg.max_new_tokens || s->frames_run >= s->cfg.max_new_tokens;
+    all_done = all_done && row_done;
+  }
+  memset(codes, 0, (size_t)B * chunk * 64);
+  memset(pcm, 0, (size_t)B * chunk * up * 4);
+  if (T > 0) {
+    // rows that are still running all have stream_emitted == frames emitted before this call
+    int f0 = -1;
+    bool same = true;
+    for (int b = 0; b < B; ++b)
+      if (len[b] > 0) { if (f0 < 0) f0 = s->stream_emitted[b]; else same = same && (f0 == s->stream_emitted[b]); }
+    Q3_REQUIRE(same, Q3_ERR_STATE, "streaming rows out of step");
+    vocode_rows(s, f0, T, len, pcm, (size_t)chunk * up);
+    for (int b = 0; b < B; ++b)
+      if (len[b] > 0)
+        Q3_CHECK_CUDA(cudaMemcpyAsync(codes + (size_t)b * chunk * 16, s->codes.as<uint32_t>() + ((size_t)b * s->frames_cap + f0) * 16,
+                                      (size_t)len[b] * 64, cudaMemcpyDeviceToHost, s->st));
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+    for (int b = 0; b < B; ++b) s->stream_emitted[b] += len[b];
+  }
+  *done = all_done ? 1 : 0;
+  Q3_API_END
+}
+
+q3_status q3_vocoder_decode(const q3_model* m, const int64_t* codes, int32_t batch, int32_t t, float* pcm) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(m && codes && pcm && batch >= 0 && t >= 0, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(m->finalized && m->has_vocoder, Q3_ERR_STATE, "model has no finalized vocoder weights");
+  if (batch == 0 || t == 0) return Q3_OK;       // codes_to_tensor of zero frames -> empty waveform
+  Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
+  std::lock_guard<std::mutex> lock(m->voc_mutex);
+  const int up = vocoder_total_upsample(m);
+  DBuf dc, dp;
+  dc.alloc((size_t)batch * m->d.v_quantizers * t * 8);
+  dp.alloc((size_t)batch * t * up * 4);
+  Q3_CHECK_CUDA(cudaMemcpy(dc.p, codes, dc.bytes, cudaMemcpyHostToDevice));
+  vocoder_run(m, m->voc_ws, dc.as<long long>(), batch, t, dp.as<float>(), 0);
+  Q3_CHECK_CUDA(cudaMemcpy(pcm, dp.p, (size_t)batch * t * up * 4, cudaMemcpyDeviceToHost));
+  Q3_API_END
+}
+
+// ---- fine-grained entry points ------------------------------------------------------------------
+q3_status q3_talker_step(q3_session* s, const uint16_t* step_input, uint16_t* hidden_out, float* logits_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && step_input, Q3_ERR_INVALID, "null argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  int max_len = 0;
+  for (int b = 0; b < s->B; ++b) max_len = std::max(max_len, s->prefill_len[b]);
+  if (max_len + s->frames_run + 1 > s->max_seq)
+    throw Q3Error(Q3_ERR_KV_OVERFLOW, "KV cache overflow: current=" + std::to_string(max_len + s->frames_run) +
+                                          " + new=1 > max=" + std::to_string(s->max_seq));
+  ensure_scratch(s, 2 * s->B);
+  bf16* x = s->sc.x.as<bf16>();
+  Q3_CHECK_CUDA(cudaMemcpyAsync(x, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
+  layers_forward(s, s->m->tl, s->m->tdims(), x, s->B, 1, s->fs.offset, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq,
+                 s->cos_tab.as<bf16>(), s->sin_tab.as<bf16>());
+  talker_head(s, x, d.hidden);
+  add_int_kernel<<<1, 256, 0, s->st>>>(s->fs.offset, s->B, 1);
+  Q3_COUNT_LAUNCH();
+  s->frames_run += 1;
+  if (hidden_out) Q3_CHECK_CUDA(cudaMemcpyAsync(hidden_out, s->last_hidden.p, (size_t)s->B * d.hidden * 2, cudaMemcpyDeviceToHost, s->st));
+  if (logits_out) Q3_CHECK_CUDA(cudaMemcpyAsync(logits_out, s->logits.p, (size_t)s->B * d.codec_vocab * 4, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  Q3_API_END
+}
+
+q3_status q3_code_predictor_frame(q3_session* s, const uint16_t* last_hidden, const uint32_t* sem_tokens, uint32_t* codes_out,
+                                  float* logits_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && last_hidden && sem_tokens && codes_out, Q3_ERR_INVALID, "null argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  const int B = s->B, n_ac = d.groups - 1;
+  for (int b = 0; b < B; ++b) Q3_REQUIRE((int)sem_tokens[b] < d.codec_vocab, Q3_ERR_INVALID, "semantic token out of range");
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->last_hidden.p, last_hidden, (size_t)B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->cur_tok.p, sem_tokens, B * 4, cudaMemcpyHostToDevice, s->st));
+  if (logits_out) s->cp_logits.ensure((size_t)n_ac * B * d.cp_vocab * 4);
+  cp_frame(s, logits_out ? s->cp_logits.as<float>() : nullptr);
+  std::vector<unsigned long long> keys((size_t)n_ac * B);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(keys.data(), s->amax.p, keys.size() * 8, cudaMemcpyDeviceToHost, s->st));
+  std::vector<float> lg;
+  if (logits_out) {
+    lg.resize((size_t)n_ac * B * d.cp_vocab);
+    Q3_CHECK_CUDA(cudaMemcpyAsync(lg.data(), s->cp_logits.p, lg.size() * 4, cudaMemcpyDeviceToHost, s->st));
+  }
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  for (int b = 0; b < B; ++b)
+    for (int g = 0; g < n_ac; ++g) {
+      codes_out[b * n_ac + g] = argmax_key_index(keys[(size_t)g * B + b]);
+      if (logits_out)
+        memcpy(logits_out + ((size_t)b * n_ac + g) * d.cp_vocab, lg.data() + ((size_t)g * B + b) * d.cp_vocab, (size_t)d.cp_vocab * 4);
+    }
+  Q3_API_END
+}
+
+q3_status q3_sample(const q3_model* m, const float* logits, int32_t batch, int32_t vocab, const q3_gen_config* cfg,
+                    uint64_t* rng_states, uint8_t* seen_mask, int32_t token_count, uint32_t* tokens_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(logits && cfg && rng_states && seen_mask && tokens_out && batch >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(vocab > 1024 && vocab <= 4096, Q3_ERR_UNSUPPORTED, "vocab must be in (1024, 4096]");
+  if (m) Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
+  DBuf dl, ds, dr, dt;
+  dl.alloc((size_t)batch * vocab * 4); ds.alloc((size_t)batch * vocab); dr.alloc(batch * 8); dt.alloc(batch * 4);
+  Q3_CHECK_CUDA(cudaMemcpy(dl.p, logits, dl.bytes, cudaMemcpyHostToDevice));
+  Q3_CHECK_CUDA(cudaMemcpy(ds.p, seen_mask, (size_t)batch * vocab, cudaMemcpyHostToDevice));
+  Q3_CHECK_CUDA(cudaMemcpy(dr.p, rng_states, batch * 8, cudaMemcpyHostToDevice));
+  SampleArgs a = make_sample_args(*cfg, vocab, batch);
+  a.logits = dl.as<float>(); a.seen = ds.as<uint8_t>(); a.rng = dr.as<unsigned long long>(); a.tok_out = dt.as<uint32_t>();
+  a.token_count = nullptr; a.token_count_imm = token_count; a.done = nullptr; a.offset = nullptr; a.frame_idx = nullptr;
+  sample_kernel<<<batch, 1024>>>(a);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  Q3_CHECK_CUDA(cudaMemcpy(tokens_out, dt.p, batch * 4, cudaMemcpyDeviceToHost));
+  Q3_CHECK_CUDA(cudaMemcpy(seen_mask, ds.p, (size_t)batch * vocab, cudaMemcpyDeviceToHost));
+  Q3_CHECK_CUDA(cudaMemcpy(rng_states, dr.p, batch * 8, cudaMemcpyDeviceToHost));
+  Q3_API_END
+}
+
+q3_status q3_fused_residual_rmsnorm(const void* x, const void* r, const void* w, void* out_normed, void* out_sum, int32_t rows,
+                                    int32_t cols, float eps, q3_dtype dtype, void* stream) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(x && r && w && out_normed && out_sum && rows >= 0 && cols >= 1, Q3_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == Q3_BF16)
+    fused_residual_rmsnorm_launch<bf16>((const bf16*)x, (const bf16*)r, (const bf16*)w, (bf16*)out_normed, (bf16*)out_sum, rows, cols, eps, st);
+  else if (dtype == Q3_F32)
+    fused_residual_rmsnorm_launch<float>((const float*)x, (const float*)r, (const float*)w, (float*)out_normed, (float*)out_sum, rows, cols, eps, st);
+  else
+    throw Q3Error(Q3_ERR_UNSUPPORTED, "fused-residual-rmsnorm unsupported dtype");
+  Q3_API_END
+}
+
+q3_status q3_fused_residual_rmsnorm_host(const void* x, const void* r, const void* w, void* out_normed, void* out_sum,
+                                         int32_t rows, int32_t cols, float eps, q3_dtype dtype, int32_t device) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(x && r && w && out_normed && out_sum && rows >= 0 && cols >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_CHECK_CUDA(cudaSetDevice(device));
+  const size_t es = dtype == Q3_BF16 ? 2 : 4, n = (size_t)rows * cols * es;
+  DBuf dx, dr, dw, dn, dsum;
+  dx.alloc(n); dr.alloc(n); dw.alloc(cols * es); dn.alloc(n); dsum.alloc(n);
+  Q3_CHECK_CUDA(cudaMemcpy(dx.p, x, n, cudaMemcpyHostToDevice));
+  Q3_CHECK_CUDA(cudaMemcpy(dr.p, r, n, cudaMemcpyHostToDevice));
+  Q3_CHECK_CUDA(cudaMemcpy(dw.p, w, cols * es, cudaMemcpyHostToDevice));
+  q3_status st = q3_fused_residual_rmsnorm(dx.p, dr.p, dw.p, dn.p, dsum.p, rows, cols, eps, dtype, nullptr);
+  if (st != Q3_OK) return st;
+  Q3_CHECK_CUDA(cudaDeviceSynchronize());
+  Q3_CHECK_CUDA(cudaMemcpy(out_normed, dn.p, n, cudaMemcpyDeviceToHost));
+  Q3_CHECK_CUDA(cudaMemcpy(out_sum, dsum.p, n, cudaMemcpyDeviceToHost));
+  Q3_API_END
+}
+
+q3_status q3_session_timing(q3_session* s, q3_timing* out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && out, Q3_ERR_INVALID, "null argument");
+  *out = s->timing;
+  Q3_API_END
+}
+
+}  // extern "C"

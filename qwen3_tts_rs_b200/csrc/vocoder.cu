@@ -1,0 +1,325 @@
+// Vocoder (Decoder12Hz) host orchestration.  ref: Decoder12Hz::{from_weights, decode}
+// (src/models/codec/decoder_12hz.rs:185-505).
+#include <algorithm>
+#include <cmath>
+
+#include "model.h"
+#include "vocoder_kernels.cuh"
+
+namespace {
+
+const RawTensor& need(const q3_model* m, const std::string& name) {
+  auto it = m->t.find(name);
+  if (it == m->t.end()) throw Q3Error(Q3_ERR_MISSING_WEIGHT, "Missing weight: " + name);
+  if (it->second.dtype != Q3_F32) throw Q3Error(Q3_ERR_INVALID, "vocoder weight must be F32: " + name);
+  return it->second;
+}
+const float* needp(const q3_model* m, const std::string& name) { return need(m, name).buf.as<float>(); }
+
+// [A][Bd][k] -> [(a or b major)...]: conv weights [Cout][Cin][k] -> [Cin*k][Cout];
+// transposed-conv weights [Cin][Cout][k] -> [Cin*k][Cout].
+__global__ void repack_conv_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int k,
+                                   int transposed) {
+  size_t n = (size_t)Cout * Cin * k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int co = (int)(i % Cout);
+    size_t r = i / Cout;
+    int j = (int)(r % k), ci = (int)(r / k);
+    size_t src = transposed ? (((size_t)ci * Cout + co) * k + j) : (((size_t)co * Cin + ci) * k + j);
+    out[i] = w[src];
+  }
+}
+
+VConv make_conv(q3_model* m, const std::string& wname, const std::string& bname, bool transposed) {
+  const RawTensor& w = need(m, wname);
+  VConv c;
+  if (w.shape.size() == 2) {               // Linear [out][in] == 1x1 conv
+    c.cout = (int)w.shape[0]; c.cin = (int)w.shape[1]; c.k = 1;
+  } else {
+    Q3_REQUIRE(w.shape.size() == 3, Q3_ERR_INVALID, "conv weight must be 3-D: " + wname);
+    c.k = (int)w.shape[2];
+    if (transposed) { c.cin = (int)w.shape[0]; c.cout = (int)w.shape[1]; }
+    else { c.cout = (int)w.shape[0]; c.cin = (int)w.shape[1]; }
+  }
+  DBuf packed;
+  packed.alloc(w.numel() * sizeof(float));
+  repack_conv_kernel<<<256, 256>>>(w.buf.as<float>(), packed.as<float>(), c.cout, c.cin, c.k, transposed ? 1 : 0);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  c.w = packed.as<float>();
+  m->owned.push_back(std::move(packed));
+  if (!bname.empty()) c.b = needp(m, bname);
+  return c;
+}
+
+VSnake make_snake(q3_model* m, const std::string& prefix) {
+  const RawTensor& a = need(m, prefix + ".alpha");
+  const RawTensor& b = need(m, prefix + ".beta");
+  int n = (int)a.numel();
+  DBuf ea, ib;
+  ea.alloc(n * sizeof(float));
+  ib.alloc(n * sizeof(float));
+  voc_prep_snake_kernel<<<ceil_div(n, 256), 256>>>(a.buf.as<float>(), b.buf.as<float>(), ea.as<float>(), ib.as<float>(), n);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  VSnake s{ea.as<float>(), ib.as<float>()};
+  m->owned.push_back(std::move(ea));
+  m->owned.push_back(std::move(ib));
+  return s;
+}
+
+void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil, const VSnake* snake, const float* res,
+                 const float* scale, int epi, cudaStream_t st) {
+  ConvArgs a;
+  a.x = x; a.w = c.w; a.bias = c.b;
+  a.snake_a = snake ? snake->ea : nullptr; a.snake_ib = snake ? snake->ib : nullptr;
+  a.res = res; a.scale = scale; a.y = y;
+  a.B = B; a.Cin = c.cin; a.Cout = c.cout; a.T = T; a.k = c.k; a.dil = dil; a.epi = epi;
+  dim3 grid(ceil_div(T, CV_BN), ceil_div(c.cout, CV_BM), B);
+  size_t smem = conv_smem_bytes(c.k, dil);
+  Q3_REQUIRE(smem <= 48 * 1024, Q3_ERR_UNSUPPORTED, "conv kernel/dilation too large for the staged tile");
+  voc_conv1d_kernel<<<grid, 256, smem, st>>>(a);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+
+void launch_tconv(const VConv& c, int stride, const float* x, float* y, int B, int T, const VSnake* snake, cudaStream_t st) {
+  Q3_REQUIRE(c.k <= 2 * stride && c.k >= stride, Q3_ERR_UNSUPPORTED, "transposed conv needs stride <= k <= 2*stride");
+  TConvArgs a;
+  a.x = x; a.w = c.w; a.bias = c.b;
+  a.snake_a = snake ? snake->ea : nullptr; a.snake_ib = snake ? snake->ib : nullptr;
+  a.y = y; a.B = B; a.Cin = c.cin; a.Cout = c.cout; a.T = T; a.k = c.k; a.stride = stride;
+  dim3 grid(ceil_div(T * stride, TC_BN), ceil_div(c.cout, TC_BM), B);
+  size_t smem = tconv_smem_bytes(c.k);
+  Q3_REQUIRE(smem <= 48 * 1024, Q3_ERR_UNSUPPORTED, "transposed conv kernel too large for the staged tile");
+  voc_tconv1d_kernel<<<grid, 256, smem, st>>>(a);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+
+void launch_norm(const float* x, const float* w, const float* b, float* y, int B, int C, int T, float eps, int mode,
+                 cudaStream_t st) {
+  dim3 grid(ceil_div(T, 32), B), block(32, 8);
+  voc_channel_norm_kernel<<<grid, block, 0, st>>>(x, w, b, y, C, T, eps, mode);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+void vocoder_codes_to_tensor(const uint32_t* frames, int frames_cap, int f0, int T, int B, long long* out, cudaStream_t st) {
+  voc_codes_to_tensor_kernel<<<dim3(ceil_div(16 * T, 256), B), 256, 0, st>>>(frames, frames_cap, f0, T, out);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+
+int vocoder_total_upsample(const q3_model* m) {
+  int n = 1;
+  for (int i = 0; i < m->d.v_n_upsampling; ++i) n *= m->d.v_upsampling[i];
+  for (int i = 0; i < m->d.v_n_rates; ++i) n *= m->d.v_rates[i];
+  return n;
+}
+
+void vocoder_finalize(q3_model* m) {
+  const q3_model_desc& d = m->d;
+  VocoderW& v = m->voc;
+  const std::string q = "decoder.quantizer";
+  // codebooks: embedding_sum / clamp(cluster_usage, 1e-7)   (decoder_12hz.rs:199-225)
+  {
+    const int rows = d.v_codebook_size, dim = d.v_vq_dim;
+    DBuf first, rest;
+    first.alloc((size_t)rows * dim * sizeof(float));
+    rest.alloc((size_t)(d.v_quantizers - 1) * rows * dim * sizeof(float));
+    auto prep = [&](const std::string& pre, float* out) {
+      const RawTensor& es = need(m, pre + "._codebook.embedding_sum");
+      const RawTensor& cu = need(m, pre + "._codebook.cluster_usage");
+      Q3_REQUIRE((int)es.numel() == rows * dim && (int)cu.numel() == rows, Q3_ERR_INVALID, "codebook shape: " + pre);
+      voc_prep_codebook_kernel<<<ceil_div(rows * dim, 256), 256>>>(es.buf.as<float>(), cu.buf.as<float>(), out, rows, dim);
+      Q3_COUNT_LAUNCH();
+      Q3_LAUNCH_CHECK();
+    };
+    prep(q + ".rvq_first.vq.layers.0", first.as<float>());
+    for (int i = 0; i < d.v_quantizers - 1; ++i)
+      prep(q + ".rvq_rest.vq.layers." + std::to_string(i), rest.as<float>() + (size_t)i * rows * dim);
+    v.first_cb = first.as<float>();
+    v.rest_cb = rest.as<float>();
+    m->owned.push_back(std::move(first));
+    m->owned.push_back(std::move(rest));
+  }
+  v.first_proj = make_conv(m, q + ".rvq_first.output_proj.weight", "", false);
+  v.rest_proj = make_conv(m, q + ".rvq_rest.output_proj.weight", "", false);
+  v.pre_conv = make_conv(m, "decoder.pre_conv.conv.weight", "decoder.pre_conv.conv.bias", false);
+  const std::string t = "decoder.pre_transformer";
+  v.in_proj = make_conv(m, t + ".input_proj.weight", t + ".input_proj.bias", false);
+  v.out_proj = make_conv(m, t + ".output_proj.weight", t + ".output_proj.bias", false);
+  v.layers.clear();
+  for (int l = 0; l < d.v_layers; ++l) {
+    const std::string p = t + ".layers." + std::to_string(l);
+    VLayer L;
+    L.in_ln = needp(m, p + ".input_layernorm.weight");
+    L.post_ln = needp(m, p + ".post_attention_layernorm.weight");
+    L.attn_scale = needp(m, p + ".self_attn_layer_scale.scale");
+    L.mlp_scale = needp(m, p + ".mlp_layer_scale.scale");
+    L.q = make_conv(m, p + ".self_attn.q_proj.weight", "", false);
+    L.k = make_conv(m, p + ".self_attn.k_proj.weight", "", false);
+    L.v = make_conv(m, p + ".self_attn.v_proj.weight", "", false);
+    L.o = make_conv(m, p + ".self_attn.o_proj.weight", "", false);
+    L.gate = make_conv(m, p + ".mlp.gate_proj.weight", "", false);
+    L.up = make_conv(m, p + ".mlp.up_proj.weight", "", false);
+    L.down = make_conv(m, p + ".mlp.down_proj.weight", "", false);
+    v.layers.push_back(L);
+  }
+  v.final_norm = needp(m, t + ".norm.weight");
+  v.ups.clear();
+  for (int s = 0; s < d.v_n_upsampling; ++s) {
+    const std::string p = "decoder.upsample." + std::to_string(s);
+    VUpsample u;
+    u.ratio = d.v_upsampling[s];
+    u.tconv = make_conv(m, p + ".0.conv.weight", p + ".0.conv.bias", true);
+    u.cn.dw_w = needp(m, p + ".1.dwconv.conv.weight");
+    u.cn.dw_b = needp(m, p + ".1.dwconv.conv.bias");
+    u.cn.ln_w = needp(m, p + ".1.norm.weight");
+    u.cn.ln_b = needp(m, p + ".1.norm.bias");
+    u.cn.gamma = needp(m, p + ".1.gamma");
+    u.cn.pw1 = make_conv(m, p + ".1.pwconv1.weight", p + ".1.pwconv1.bias", false);
+    u.cn.pw2 = make_conv(m, p + ".1.pwconv2.weight", p + ".1.pwconv2.bias", false);
+    u.cn.C = u.tconv.cout;
+    v.ups.push_back(u);
+  }
+  v.init_conv = make_conv(m, "decoder.decoder.0.conv.weight", "decoder.decoder.0.conv.bias", false);
+  v.blocks.clear();
+  for (int b = 0; b < d.v_n_rates; ++b) {
+    const std::string bp = "decoder.decoder." + std::to_string(b + 1) + ".block";
+    VBlock blk;
+    blk.rate = d.v_rates[b];
+    blk.s = make_snake(m, bp + ".0");
+    blk.up = make_conv(m, bp + ".1.conv.weight", bp + ".1.conv.bias", true);
+    const int dils[3] = {1, 3, 9};
+    for (int u = 0; u < 3; ++u) {
+      const std::string up = bp + "." + std::to_string(u + 2);
+      blk.ru[u].a1 = make_snake(m, up + ".act1");
+      blk.ru[u].c1 = make_conv(m, up + ".conv1.conv.weight", up + ".conv1.conv.bias", false);
+      blk.ru[u].a2 = make_snake(m, up + ".act2");
+      blk.ru[u].c2 = make_conv(m, up + ".conv2.conv.weight", up + ".conv2.conv.bias", false);
+      blk.ru[u].dil = dils[u];
+    }
+    v.blocks.push_back(blk);
+  }
+  const std::string fs = "decoder.decoder." + std::to_string(d.v_n_rates + 1);
+  const std::string fc = "decoder.decoder." + std::to_string(d.v_n_rates + 2);
+  v.final_snake = make_snake(m, fs);
+  v.final_conv = make_conv(m, fc + ".conv.weight", fc + ".conv.bias", false);
+  Q3_CHECK_CUDA(cudaDeviceSynchronize());
+  m->has_vocoder = true;
+}
+
+// Largest [C][T'] activation (floats per batch row) for T frames.
+static size_t vocoder_max_act(const q3_model* m, int T) {
+  const q3_model_desc& d = m->d;
+  size_t mx = (size_t)std::max(std::max(std::max(d.v_latent_dim, d.v_codebook_dim), d.v_heads * d.v_head_dim), std::max(d.v_inter, d.v_hidden)) * T;
+  int len = T;
+  int c = d.v_latent_dim;
+  for (int s = 0; s < d.v_n_upsampling; ++s) {
+    len *= d.v_upsampling[s];
+    mx = std::max(mx, (size_t)4 * c * len);       // ConvNeXt expansion
+  }
+  c = d.v_decoder_dim;
+  mx = std::max(mx, (size_t)c * len);
+  for (int b = 0; b < d.v_n_rates; ++b) {
+    len *= d.v_rates[b];
+    c /= 2;
+    mx = std::max(mx, (size_t)c * len);
+  }
+  return mx;
+}
+
+void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes, int B, int T, float* pcm, cudaStream_t st) {
+  Q3_REQUIRE(m->has_vocoder, Q3_ERR_STATE, "vocoder weights were not loaded");
+  if (B <= 0 || T <= 0) return;
+  const q3_model_desc& d = m->d;
+  const VocoderW& v = m->voc;
+  Q3_REQUIRE(T <= 3072, Q3_ERR_UNSUPPORTED, "vocoder: at most 3072 frames per call");
+  const size_t act = vocoder_max_act(m, T) * (size_t)B * sizeof(float);
+  ws.a.ensure(act); ws.b.ensure(act); ws.c.ensure(act); ws.d.ensure(act);
+  const int AD = d.v_heads * d.v_head_dim;
+  ws.e_first.ensure((size_t)B * d.v_vq_dim * T * sizeof(float));
+  ws.e_rest.ensure((size_t)B * d.v_vq_dim * T * sizeof(float));
+  ws.qh.ensure((size_t)B * AD * T * sizeof(float));
+  ws.kh.ensure((size_t)B * AD * T * sizeof(float));
+  ws.vh.ensure((size_t)B * AD * T * sizeof(float));
+  float *A = ws.a.as<float>(), *Bf = ws.b.as<float>(), *C = ws.c.as<float>(), *D = ws.d.as<float>();
+
+  // 1. RVQ decode: first_proj(E_first) + rest_proj(sum E_rest)   (decoder_12hz.rs:420-450)
+  voc_rvq_gather_kernel<<<dim3(T, B), 128, 0, st>>>(codes, v.first_cb, v.rest_cb, d.v_quantizers, d.v_codebook_size,
+                                                   d.v_vq_dim, T, ws.e_first.as<float>(), ws.e_rest.as<float>());
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  launch_conv(v.first_proj, ws.e_first.as<float>(), A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  launch_conv(v.rest_proj, ws.e_rest.as<float>(), Bf, B, T, 1, nullptr, A, nullptr, CEPI_NONE, st);   // Bf = A + rest
+  // 2. pre_conv (k3) -> C ; 3. input_proj -> A (hidden 512)
+  launch_conv(v.pre_conv, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  launch_conv(v.in_proj, C, A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  // transformer layers (decoder_12hz.rs:586-672); hidden lives in A
+  const float scale = 1.0f / sqrtf((float)d.v_head_dim);
+  Q3_REQUIRE((size_t)4 * T * sizeof(float) <= 48 * 1024, Q3_ERR_UNSUPPORTED, "vocoder attention: T too large");
+  for (const VLayer& L : v.layers) {
+    launch_norm(A, L.in_ln, nullptr, Bf, B, d.v_hidden, T, d.v_rms_eps, 0, st);
+    launch_conv(L.q, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.qh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 1);
+    Q3_COUNT_LAUNCH();
+    launch_conv(L.k, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.kh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 1);
+    Q3_COUNT_LAUNCH();
+    launch_conv(L.v, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.vh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 0);
+    Q3_COUNT_LAUNCH();
+    voc_attn_kernel<<<dim3(ceil_div(T, 4), d.v_heads, B), 128, (size_t)4 * T * sizeof(float), st>>>(
+        ws.qh.as<float>(), ws.kh.as<float>(), ws.vh.as<float>(), C, d.v_heads, d.v_head_dim, T, scale);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    launch_conv(L.o, C, D, B, T, 1, nullptr, A, L.attn_scale, CEPI_NONE, st);        // D = A + scale*o_proj
+    launch_norm(D, L.post_ln, nullptr, Bf, B, d.v_hidden, T, d.v_rms_eps, 0, st);
+    launch_conv(L.gate, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+    launch_conv(L.up, Bf, A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+    {
+      size_t n = (size_t)B * d.v_inter * T;
+      voc_silu_mul_kernel<<<(int)std::min<size_t>(4096, (n + 255) / 256), 256, 0, st>>>(C, A, C, n);
+      Q3_COUNT_LAUNCH();
+      Q3_LAUNCH_CHECK();
+    }
+    launch_conv(L.down, C, A, B, T, 1, nullptr, D, L.mlp_scale, CEPI_NONE, st);      // A = D + scale*down
+  }
+  launch_norm(A, v.final_norm, nullptr, Bf, B, d.v_hidden, T, d.v_rms_eps, 0, st);
+  launch_conv(v.out_proj, Bf, A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);   // [B][1024][T]
+  // upsample stages: transconv + ConvNeXt
+  int len = T;
+  float* cur = A;
+  float* o1 = Bf;
+  float* o2 = C;
+  float* o3 = D;
+  for (const VUpsample& u : v.ups) {
+    launch_tconv(u.tconv, u.ratio, cur, o1, B, len, nullptr, st);
+    len *= u.ratio;
+    const int Cn = u.cn.C;
+    voc_dwconv_kernel<<<dim3(ceil_div(len, 256), B * Cn), 256, 0, st>>>(o1, u.cn.dw_w, u.cn.dw_b, o2, Cn, len, 7);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    launch_norm(o2, u.cn.ln_w, u.cn.ln_b, o3, B, Cn, len, 1e-6f, 1, st);
+    launch_conv(u.cn.pw1, o3, o2, B, len, 1, nullptr, nullptr, nullptr, CEPI_GELU, st);
+    launch_conv(u.cn.pw2, o2, cur, B, len, 1, nullptr, o1, u.cn.gamma, CEPI_NONE, st);   // cur = o1 + gamma*pw2
+  }
+  launch_conv(v.init_conv, cur, o1, B, len, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  std::swap(cur, o1);
+  for (const VBlock& blk : v.blocks) {
+    launch_tconv(blk.up, blk.rate, cur, o1, B, len, &blk.s, st);
+    len *= blk.rate;
+    std::swap(cur, o1);
+    for (int r = 0; r < 3; ++r) {
+      const VResUnit& ru = blk.ru[r];
+      launch_conv(ru.c1, cur, o1, B, len, ru.dil, &ru.a1, nullptr, nullptr, CEPI_NONE, st);
+      launch_conv(ru.c2, o1, o2, B, len, 1, &ru.a2, cur, nullptr, CEPI_NONE, st);        // o2 = cur + conv2
+      std::swap(cur, o2);
+    }
+  }
+  launch_conv(v.final_conv, cur, pcm, B, len, 1, &v.final_snake, nullptr, nullptr, CEPI_CLAMP, st);
+}

@@ -171,3 +171,12 @@ def special_text_id(spec: ModelSpec, tok: int) -> int:
     if spec.text_vocab == 151936:
         return tok
     return tok - 151936 + spec.text_vocab if tok >= 151643 else tok % (spec.text_vocab - 300)
+
+
+# mid-size spec: hidden >= 1024 exercises the 128-thread reference-order RMSNorm path and the
+# small_to_mtp projection, still cheap enough for the CPU oracle.
+SPEC_MID = ModelSpec(name="mid", hidden=2048, inter=1024, layers=2, heads=4, kv_heads=2,
+                     text_vocab=2048, text_embed_dim=256,
+                     cp_hidden=1024, cp_inter=1024, cp_layers=2, cp_heads=4, cp_kv_heads=2,
+                     vocoder=TINY_VOCODER)
+SPECS["mid"] = SPEC_MID

