@@ -89,11 +89,18 @@ def generate_codes(talker: Talker, cp: CodePredictor, cfg: smp.GenerationConfig,
         l2 = smp.apply_generation_penalties(raw, penalty_mask, cfg, token_count, suppression)
         rng_state_before = ctx.state
         next_tok = int(smp.sample(l2, cfg, ctx)[0])
+        sample_margin = None
+        if trace is not None and cfg.temperature >= 0.01:
+            # distance of this draw from the nearest CDF boundary (exemption measure for bf16 logit noise)
+            probe = smp.SamplingContext(0)
+            probe.state = rng_state_before
+            _, dbg = smp.sample_row(l2[0], cfg, probe.rand_f32(), return_debug=True)
+            sample_margin = dbg["margin"]
         if trace is not None:
             trace.frames.append(dict(frame=frame_idx, tok=tok, codes=codes, cp_in_hidden=last_hidden.clone(),
                                      cp_logits=cp_logits, step_input=step_input.clone(), hidden=h.clone(),
                                      logits=raw.copy(), penalised=l2.copy(), rng_state=rng_state_before,
-                                     next_tok=next_tok))
+                                     next_tok=next_tok, sample_margin=sample_margin))
         last_hidden = h
         tok = next_tok
         smp.update_penalty_mask(penalty_mask, tok)

@@ -182,7 +182,12 @@ def make_tensor(name: str, shape: tuple, kind: str, base_seed: int = BASE_SEED) 
         return _normal(name, shape, 1.0, base_seed)
     if kind == "conv":      # [C_out, C_in/groups, k]
         fan = shape[1] * shape[2]
-        return _normal(name, shape, 1.0 / math.sqrt(fan), base_seed)
+        gain = 1.0
+        if name.endswith("conv2.conv.weight"):
+            gain = 0.25     # residual branch: keeps the activation scale flat across the 12 residual units
+        if shape[0] == 1:
+            gain = 0.1      # final conv: PCM rms ~0.25 so the [-1,1] clamp is rarely active
+        return _normal(name, shape, gain / math.sqrt(fan), base_seed)
     if kind == "tconv":     # [C_in, C_out, k]; each output sample sees C_in * ceil(k/stride) taps
         fan = shape[0] * 2 if shape[2] > 2 else shape[0]
         return _normal(name, shape, 1.0 / math.sqrt(fan), base_seed)
