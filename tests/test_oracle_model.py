@@ -1,0 +1,255 @@
+"""CPU tests of the oracle against the weight-free known answers in the reference's unit tests
+ and against an independent implementation of the same model family
+(transformers' qwen3_omni_moe Code2Wav blocks) for block semantics."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import generate as OG
+from oracle import model as OM
+from oracle import sampling as osmp
+from oracle import vocoder as OV
+from qwen3_tts_rs_b200 import spec as S, weights as W
+from conftest import talker_weights, vocoder_weights
+
+
+# ---- causal conv / trans conv / snake (causal_conv.rs:154-238, causal_trans_conv.rs:119-197, snake_beta.rs:107-132)
+@pytest.mark.parametrize("k,dil", [(1, 1), (3, 1), (7, 1), (7, 3), (7, 9)])
+def test_causal_conv_length_and_causality(k, dil):
+    g = torch.Generator().manual_seed(0)
+    w, b = torch.randn(5, 4, k, generator=g), torch.randn(5, generator=g)
+    x = torch.randn(2, 4, 20, generator=g)
+    y = OV.causal_conv1d(x, w, b, dil)
+    assert y.shape == (2, 5, 20)
+    x2 = x.clone()
+    x2[:, :, 12:] += 1.0                      # changing the future must not change the past
+    y2 = OV.causal_conv1d(x2, w, b, dil)
+    assert torch.equal(y[:, :, :12], y2[:, :, :12]) and not torch.equal(y[:, :, 12:], y2[:, :, 12:])
+
+
+@pytest.mark.parametrize("k,s", [(16, 8), (10, 5), (8, 4), (6, 3), (4, 2), (2, 2)])
+def test_causal_trans_conv_lengths(k, s):
+    x = torch.randn(1, 3, 7)
+    w = torch.randn(3, 2, k)
+    y = OV.causal_trans_conv1d(x, w, None, s)
+    assert y.shape == (1, 2, 7 * s)           # right_trim = k - s (causal_trans_conv.rs:86)
+    x2 = x.clone()
+    x2[:, :, 4:] += 1.0
+    y2 = OV.causal_trans_conv1d(x2, w, None, s)
+    assert torch.equal(y[:, :, : 4 * s], y2[:, :, : 4 * s])
+
+
+def test_snake_beta_zero_params():
+    x = torch.linspace(-3, 3, 50).reshape(1, 2, 25)
+    y = OV.snake_beta(x, torch.zeros(2), torch.zeros(2))
+    assert torch.allclose(y, x + torch.sin(x) ** 2, atol=1e-6)     # alpha = beta = 0 -> x + sin^2 x
+
+
+def test_upsample_total_and_stage_shapes():
+    """decoder_12hz.rs:713-722 (total 1920) and the T=2 stage shapes asserted in reference_validation.rs
+    (SURVEY.md §4): quantized [1,512,2], pre_conv [1,1024,2], pre_transformer [1,2,512], output_proj
+    [1,2,1024], upsample_0 [1,1024,4], decoder.0 [1,1536,8], decoder.1 [1,768,64]; 1 frame -> 1920, 2 -> 3840."""
+    vs = S.VocoderSpec()
+    assert vs.total_upsample == 1920
+    vw = vocoder_weights(vs, "full")
+    voc = OV.Vocoder(vs, vw)
+    st = {}
+    out = voc.decode(np.zeros((1, 16, 2), dtype=np.int64), st)
+    assert out.shape == (1, 1, 3840)
+    assert tuple(st["quantized"].shape) == (1, 512, 2)
+    assert tuple(st["pre_conv"].shape) == (1, 1024, 2)
+    assert tuple(st["pre_transformer"].shape) == (1, 2, 512)
+    assert tuple(st["output_proj"].shape) == (1, 2, 1024)
+    assert tuple(st["upsample_0"].shape) == (1, 1024, 4)
+    assert tuple(st["decoder.0"].shape) == (1, 1536, 8)
+    assert tuple(st["decoder.1"].shape) == (1, 768, 64)
+    assert voc.decode(np.zeros((1, 16, 1), dtype=np.int64)).shape == (1, 1, 1920)
+    assert float(out.abs().max()) <= 1.0
+
+
+def test_decoder_block_length():                  # decoder_block.rs:298-376
+    vs = S.TINY_VOCODER
+    vw = vocoder_weights(vs, "tiny")
+    x = torch.randn(1, vs.decoder_dim, 5)
+    y = OV.decoder_block(x, vw, "decoder.decoder.1.block", 8)
+    assert y.shape == (1, vs.decoder_dim // 2, 40)
+
+
+def test_vocoder_blocks_match_transformers_code2wav():
+    """Independent cross-check of block semantics against transformers' qwen3_omni_moe (same model family):
+    SnakeBeta, the causal conv net, the causal transposed conv (right trim), the residual unit and the
+    ConvNeXt block.  Where the two could differ the Rust reference wins, so only blocks whose
+    definitions coincide are compared."""
+    mod = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    g = torch.Generator().manual_seed(1)
+    # SnakeBeta
+    sb = mod.SnakeBeta(6)
+    with torch.no_grad():
+        sb.alpha.copy_(0.1 * torch.randn(6, generator=g))
+        sb.beta.copy_(0.1 * torch.randn(6, generator=g))
+    x = torch.randn(2, 6, 11, generator=g)
+    assert torch.allclose(sb(x), OV.snake_beta(x, sb.alpha.detach(), sb.beta.detach()), atol=1e-6)
+    # causal conv, dilation 3
+    cc = mod.Qwen3OmniMoeCausalConvNet(6, 4, kernel_size=7, dilation=3)
+    y = cc(x)
+    assert torch.allclose(y, OV.causal_conv1d(x, cc.conv.weight.detach(), cc.conv.bias.detach(), 3), atol=1e-5)
+    # causal transposed conv k = 2*s
+    tc = mod.Qwen3OmniMoeCausalTransConvNet(6, 4, 10, 5)
+    y = tc(x)
+    mine = OV.causal_trans_conv1d(x, tc.conv.weight.detach(), tc.conv.bias.detach(), 5)
+    # transformers trims k - s from BOTH sides (50 samples); the Rust reference trims the right side only and
+    # keeps exactly T*s samples (causal_trans_conv.rs:86-100, docs/VALIDATION.md:79-96) -- the reference wins;
+    # the two agree on the overlapping samples.
+    assert mine.shape == (2, 4, 55) and y.shape == (2, 4, 50) and torch.allclose(y, mine[:, :, 5:], atol=1e-5)
+    # residual unit
+    ru = mod.Qwen3OmniMoeCode2WavDecoderResidualUnit(6, 9)
+    w = {"u.act1.alpha": ru.act1.alpha.detach(), "u.act1.beta": ru.act1.beta.detach(),
+         "u.conv1.conv.weight": ru.conv1.conv.weight.detach(), "u.conv1.conv.bias": ru.conv1.conv.bias.detach(),
+         "u.act2.alpha": ru.act2.alpha.detach(), "u.act2.beta": ru.act2.beta.detach(),
+         "u.conv2.conv.weight": ru.conv2.conv.weight.detach(), "u.conv2.conv.bias": ru.conv2.conv.bias.detach()}
+    xx = torch.randn(1, 6, 40, generator=g)
+    assert torch.allclose(ru(xx), OV.residual_unit(xx, w, "u", 9), atol=1e-5)
+    # ConvNeXt block
+    cn = mod.Qwen3OmniMoeConvNeXtBlock(6)
+    with torch.no_grad():
+        cn.gamma.copy_(0.1 + 0.02 * torch.randn(6, generator=g))
+    w = {"c.dwconv.conv.weight": cn.dwconv.conv.weight.detach(), "c.dwconv.conv.bias": cn.dwconv.conv.bias.detach(),
+         "c.norm.weight": cn.norm.weight.detach(), "c.norm.bias": cn.norm.bias.detach(),
+         "c.pwconv1.weight": cn.pwconv1.weight.detach(), "c.pwconv1.bias": cn.pwconv1.bias.detach(),
+         "c.pwconv2.weight": cn.pwconv2.weight.detach(), "c.pwconv2.bias": cn.pwconv2.bias.detach(),
+         "c.gamma": cn.gamma.detach()}
+    assert torch.allclose(cn(xx), OV.convnext_block(xx, w, "c"), atol=1e-5)
+
+
+# ---- transformer pieces ---------------------------------------------------------------------------------
+def test_fused_equals_sequential_rmsnorm_f32():      # fused_ops.rs:269-313
+    g = torch.Generator().manual_seed(3)
+    x, r = torch.randn(4, 64, generator=g), torch.randn(4, 64, generator=g)
+    w = 1 + 0.1 * torch.randn(64, generator=g)
+    n1, s1 = OM.fused_residual_rmsnorm(OM.F32P, x, r, w, 1e-6, cuda_kernel_semantics=True)
+    n2, s2 = OM.fused_residual_rmsnorm(OM.F32P, x, r, w, 1e-6, cuda_kernel_semantics=False)
+    assert torch.equal(s1, x + r) and torch.allclose(n1, n2, atol=1e-5)
+    assert torch.allclose(n1, OM.rms_norm(OM.F32P, x + r, w, 1e-6), atol=1e-6)
+
+
+def test_fused_bf16_quirk_sum_of_unrounded():
+    """fused_residual_rmsnorm.cu:60-65,86: sum of squares from the un-rounded f32 sum, output from the rounded one."""
+    x = torch.tensor([[1.0, 2.0 ** -9]]).to(torch.bfloat16).float()
+    r = torch.tensor([[2.0 ** -9, 1.0]]).to(torch.bfloat16).float()
+    w = torch.ones(2)
+    n, s = OM.fused_residual_rmsnorm(OM.BF16P, x, r, w, 0.0)
+    assert torch.equal(s, torch.tensor([[1.0, 1.0]]))           # 1 + 2^-9 rounds to 1 in bf16
+    exact = (1 + 2.0 ** -9)
+    assert torch.allclose(n, OM.BF16P.r(torch.tensor([[1.0, 1.0]]) / exact), atol=0)
+
+
+def test_kv_cache_semantics():                       # kv_cache.rs:378-389, 293-300, 350-352
+    c = OM.KVCache(max_seq=7)
+    k1 = torch.randn(1, 2, 4, 16)
+    k, v = c.update(k1, k1)
+    assert k.shape == (1, 2, 4, 16)
+    k, v = c.update(torch.randn(1, 2, 3, 16), torch.randn(1, 2, 3, 16))
+    assert k.shape == (1, 2, 7, 16) and torch.equal(k[:, :, :4], k1)
+    with pytest.raises(RuntimeError, match="KV cache overflow"):
+        c.update(torch.randn(1, 2, 1, 16), torch.randn(1, 2, 1, 16))
+    c.reset()
+    assert len(c) == 0
+
+
+def test_causal_mask():                              # transformer.rs:21-36
+    m = OM.causal_mask(3, 2)[0, 0]
+    assert m.shape == (3, 5)
+    assert (m[0] == torch.tensor([0, 0, 0, float("-inf"), float("-inf")])).all()
+    assert (m[2] == 0).all()
+
+
+def test_rope_is_rotation_and_position_zero_is_identity():
+    cos, sin = OM.rope_cos_sin([0, 5], 128, 1e6)
+    x = torch.randn(1, 2, 2, 128)
+    y = OM.apply_rope_rotation(OM.F32P, x, cos, sin)
+    assert torch.allclose(y[:, :, 0], x[:, :, 0], atol=1e-6)
+    assert torch.allclose(y.norm(dim=-1), x.norm(dim=-1), atol=1e-4)
+    assert float(OM.inv_freq(128, 1e6)[0]) == 1.0
+
+
+def test_prefill_then_steps_equals_full_prefill_f32():
+    """Decode steps over the KV cache reproduce a longer causal prefill (the cache/rope/mask plumbing)."""
+    spec = S.SPEC_TINY
+    tk, _ = OM.Talker(spec, talker_weights(spec), OM.F32P), None
+    g = torch.Generator().manual_seed(5)
+    emb = 0.05 * torch.randn(1, 6, spec.hidden, generator=g)
+    c1 = tk.new_kv_caches()
+    h_full, logits_full = tk.run_prefill_layers(emb, c1)
+    c2 = tk.new_kv_caches()
+    tk.run_prefill_layers(emb[:, :4], c2)
+    h4, _ = tk.generate_step_with_embed(emb[:, 4:5], c2, 4)
+    h5, l5 = tk.generate_step_with_embed(emb[:, 5:6], c2, 5)
+    assert torch.allclose(h5, h_full[:, 5:6], atol=2e-5) and torch.allclose(l5, logits_full, atol=2e-4)
+
+
+def test_custom_voice_prefill_is_10_positions_and_voice_design_layout():
+    """talker.rs:437-449: 3 role + 6 codec/tts + 1 first-text = 10 positions whatever the text length;
+    VoiceDesign: N_instruct + 9 (talker.rs:566-583)."""
+    spec = S.SPEC_TINY
+    tk = OM.Talker(spec, talker_weights(spec), OM.BF16P)
+    for n in (1, 5, 40):
+        e = tk.custom_voice_embeds(list(range(n)), S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+        assert e.shape == (1, 10, spec.hidden)
+    e = tk.voice_design_embeds([1, 2, 3], list(range(24)), S.LANGUAGE_IDS["english"])
+    assert e.shape == (1, 24 + 9, spec.hidden)
+    t, n, pad = tk.build_trailing_text([7])
+    assert n == 1 and torch.equal(t, tk.tts_eos_embed())            # lib.rs:509-515
+    t, n, pad = tk.build_trailing_text([7, 8, 9])
+    assert n == 3 and torch.equal(t[:, 2:3], tk.tts_eos_embed())
+
+
+def test_generate_loop_semantics_f32():
+    """generate_codes (lib.rs:530-656): frames are [semantic, a0..a14]; acoustic codes < 2048; semantic ids never
+    in the suppressed range; frame count == max_new_tokens without EOS; seeded determinism; F32 and BF16 modes
+    both run."""
+    spec = S.SPEC_TINY
+    w = talker_weights(spec)
+    ids = W.synthetic_prompt(1, spec)
+    for prec in (OM.F32P, OM.BF16P):
+        tk, cp = OM.Talker(spec, w, prec), OM.CodePredictor(spec, w, prec)
+        emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+        cfg = osmp.GenerationConfig(max_new_tokens=5)
+        a = OG.prefill_and_generate(tk, cp, emb, ids, cfg, 42)
+        b = OG.prefill_and_generate(tk, cp, emb, ids, cfg, 42)
+        assert a == b and len(a) == 5 and all(len(f) == 16 for f in a)
+        assert all(f[0] < 2048 or f[0] == 2150 for f in a) and all(max(f[1:]) < 2048 for f in a)
+        c = OG.prefill_and_generate(tk, cp, emb, ids, cfg, 43)
+        assert c != a
+
+
+def test_forced_eos_stops_the_loop():
+    """+40 on logit 2150 at frame 3 -> the loop stops; the EOS frame is not emitted."""
+    spec = S.SPEC_TINY
+    w = talker_weights(spec)
+    tk, cp = OM.Talker(spec, w, OM.F32P), OM.CodePredictor(spec, w, OM.F32P)
+    ids = W.synthetic_prompt(0, spec)
+    emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+
+    def hook(frame_idx, logits):
+        if frame_idx == 3:
+            logits = logits.copy()
+            logits[:, 2150] += 40.0
+        return logits
+    fr = OG.prefill_and_generate(tk, cp, emb, ids, osmp.GenerationConfig(max_new_tokens=10), 42, logit_hook=hook)
+    assert len(fr) == 4 and all(f[0] != 2150 for f in fr)
+
+
+def test_streaming_session_chunks():
+    """lib.rs:1650-1759: chunk_frames buffering, flush of the remainder, frame count equals non-streaming."""
+    spec = S.SPEC_TINY
+    w = talker_weights(spec)
+    tk, cp = OM.Talker(spec, w, OM.F32P), OM.CodePredictor(spec, w, OM.F32P)
+    ids = W.synthetic_prompt(2, spec)
+    emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+    cfg = osmp.GenerationConfig(max_new_tokens=7)
+    s = OG.StreamingSession(tk, cp, lambda c: np.zeros(c.shape[2] * 1920, np.float32), emb, ids, cfg, 5, chunk_frames=3)
+    chunks = list(s)
+    assert [len(c) // 1920 for c in chunks] == [3, 3, 1]
+    ref = OG.prefill_and_generate(tk, cp, emb, ids, cfg, 5)
+    assert s.all_frames == ref
