@@ -315,33 +315,33 @@ __global__ void cp_embed_kernel(FrameState st, const bf16* __restrict__ emb_g, b
 //   acc = E0[a0]; acc = bf16(acc + Ei[ai]) (i = 1..14, in order); summed = bf16(sem + acc);
 //   step_input = bf16(summed + (frame_idx < lt ? trailing[frame_idx] : tts_pad)).
 struct EmbTable { const bf16* e[15]; };
-__global__ void frame_finish_kernel(FrameState st, EmbTable tab, const bf16* __restrict__ codec_emb,
-                                    bf16* __restrict__ step_input, int H, int B, int n_ac) {
-  const int b = blockIdx.x;
-  __shared__ uint32_t codes[16];
+// body for one row b, executed by a whole block; codes_sm: 16 x u32 of shared memory
+__device__ __forceinline__ void frame_finish_row(const FrameState& st, const EmbTable& tab, const bf16* __restrict__ codec_emb,
+                                                 bf16* __restrict__ step_input, int H, int B, int n_ac, int b,
+                                                 uint32_t* codes_sm) {
   if (threadIdx.x < 16) {
     uint32_t c;
     if (threadIdx.x == 0) c = st.cur_tok[b];
     else if (threadIdx.x < n_ac) c = st.frame_codes[b * 16 + threadIdx.x];
     else c = argmax_key_index(st.amax[(size_t)(n_ac - 1) * B + b]);
-    codes[threadIdx.x] = c;
+    codes_sm[threadIdx.x] = c;
   }
   __syncthreads();
   const int fi = st.frame_idx[b];
   const bool active = !st.done[b];
   if (active && threadIdx.x < 16 && fi < st.frames_cap)
-    st.codes[((size_t)b * st.frames_cap + fi) * 16 + threadIdx.x] = codes[threadIdx.x];
+    st.codes[((size_t)b * st.frames_cap + fi) * 16 + threadIdx.x] = codes_sm[threadIdx.x];
   if (active && threadIdx.x == 0) st.n_frames[b] = fi + 1;
   const bf16* text = (fi < st.lt[b]) ? st.trailing + ((size_t)b * st.lt_max + fi) * H : st.tts_pad;
   for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) {
     float acc[8], f[8];
-    unpack8(*reinterpret_cast<const uint4*>(tab.e[0] + (size_t)codes[1] * H + c), acc);
+    unpack8(*reinterpret_cast<const uint4*>(tab.e[0] + (size_t)codes_sm[1] * H + c), acc);
     for (int i = 1; i < n_ac; ++i) {
-      unpack8(*reinterpret_cast<const uint4*>(tab.e[i] + (size_t)codes[1 + i] * H + c), f);
+      unpack8(*reinterpret_cast<const uint4*>(tab.e[i] + (size_t)codes_sm[1 + i] * H + c), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = rbf(acc[e] + f[e]);
     }
-    unpack8(*reinterpret_cast<const uint4*>(codec_emb + (size_t)codes[0] * H + c), f);
+    unpack8(*reinterpret_cast<const uint4*>(codec_emb + (size_t)codes_sm[0] * H + c), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = rbf(f[e] + acc[e]);
     unpack8(*reinterpret_cast<const uint4*>(text + c), f);
@@ -349,6 +349,13 @@ __global__ void frame_finish_kernel(FrameState st, EmbTable tab, const bf16* __r
     for (int e = 0; e < 8; ++e) acc[e] = rbf(acc[e] + f[e]);
     *reinterpret_cast<uint4*>(step_input + (size_t)b * H + c) = pack8(acc);
   }
+  __syncthreads();
+}
+
+__global__ void frame_finish_kernel(FrameState st, EmbTable tab, const bf16* __restrict__ codec_emb,
+                                    bf16* __restrict__ step_input, int H, int B, int n_ac) {
+  __shared__ uint32_t codes[16];
+  frame_finish_row(st, tab, codec_emb, step_input, H, B, n_ac, blockIdx.x, codes);
 }
 
 // gather row (b, lens[b]-1) of a [B][l_max][H] tensor
@@ -418,18 +425,30 @@ struct SampleArgs {
   int advance;              // 1: this is a loop iteration (advance offset / frame_idx)
 };
 
-__global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
-  __shared__ float xs[4096];       // penalised / tempered logits, vocab order
-  __shared__ float srt[4096];      // sorted descending; reused as kept_e once the thresholds are known
-  __shared__ unsigned short kept_idx[4096];
+// Shared-memory scratch of one sampler row: 4096 + 4096 floats, 4096 u16, 4 scalars (40976 bytes).
+struct SampleSmem {
+  float xs[4096];                  // penalised / tempered logits, vocab order
+  float srt[4096];                 // sorted descending; reused as kept_e once the thresholds are known
+  unsigned short kept_idx[4096];
+  float s_thr, s_mx;
+  int s_nkept, s_tok;
+};
+
+// One row, executed by a whole block of any size that is a multiple of 32.
+__device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b, SampleSmem& sm) {
+  float* xs = sm.xs;
+  float* srt = sm.srt;
+  unsigned short* kept_idx = sm.kept_idx;
   float* kept_e = srt;
-  __shared__ float s_thr, s_mx;
-  __shared__ int s_nkept, s_tok;
-  const int b = blockIdx.x, tid = threadIdx.x, V = a.V;
+  float& s_thr = sm.s_thr;
+  float& s_mx = sm.s_mx;
+  int& s_nkept = sm.s_nkept;
+  int& s_tok = sm.s_tok;
+  const int tid = threadIdx.x, V = a.V, NT = blockDim.x;
   const float* lg = a.logits + (size_t)b * V;
   uint8_t* seen = a.seen + (size_t)b * V;
   const int tcount = a.token_count ? a.token_count[b] : a.token_count_imm;
-  for (int i = tid; i < 4096; i += 1024) {
+  for (int i = tid; i < 4096; i += NT) {
     float x = -INFINITY;
     if (i < V) {
       x = lg[i];
@@ -445,7 +464,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
   if (a.greedy) {                                                                 // sampling.rs:155-157
     // arg-max, lowest index among ties
     unsigned long long best = 0ull;
-    for (int i = tid; i < V; i += 1024) {
+    for (int i = tid; i < V; i += NT) {
       unsigned long long k = argmax_key(xs[i], i);
       best = k > best ? k : best;
     }
@@ -458,7 +477,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
     if ((tid & 31) == 0) red[tid >> 5] = best;
     __syncthreads();
     if (tid == 0) {
-      for (int w = 1; w < 32; ++w) best = red[w] > best ? red[w] : best;
+      for (int w = 1; w < (NT >> 5); ++w) best = red[w] > best ? red[w] : best;
       s_tok = (int)argmax_key_index(best);
     }
     __syncthreads();
@@ -466,7 +485,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
     // bitonic sort, descending, 4096 keys / 1024 threads
     for (int k = 2; k <= 4096; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < 4096; i += 1024) {
+        for (int i = tid; i < 4096; i += NT) {
           int ixj = i ^ j;
           if (ixj > i) {
             float x = srt[i], y = srt[ixj];
@@ -565,6 +584,11 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
       if (a.eos >= 0 && tok == a.eos) a.done[b] = 1;            // lib.rs:581-585 (tested next iteration)
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
+  __shared__ SampleSmem sm;
+  sample_row_body(a, blockIdx.x, sm);
 }
 
 // number of rows still running -> mapped host flag (polled every few frames by the host loop)

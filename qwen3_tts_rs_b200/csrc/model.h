@@ -83,6 +83,7 @@ struct q3_model {
   const bf16* cp_emb[15] = {nullptr};
   const bf16* cp_head[15] = {nullptr};
   std::vector<LayerW> cl;
+  const LayerW *tl_dev = nullptr, *cl_dev = nullptr;   // device copies of the layer tables (persistent kernel)
   const bf16 *cp_cos = nullptr, *cp_sin = nullptr;   // [cp_rope_positions][64]
   bool has_talker = false, has_vocoder = false;
   VocoderW voc;

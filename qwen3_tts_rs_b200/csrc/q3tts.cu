@@ -5,8 +5,11 @@
 #include <cmath>
 #include <cstring>
 
+#include <cstdlib>
+
 #include "decode_kernels.cuh"
 #include "gemv.cuh"
+#include "mega.cuh"
 #include "model.h"
 
 std::atomic<uint64_t> g_q3_launches{0};
@@ -38,6 +41,11 @@ struct q3_session {
   std::vector<int> prefill_len;
   int frames_run = 0;              // loop iterations executed since prefill
   bool prefilled = false, first_sampled = false;
+  // persistent frame kernel (batch <= 8)
+  bool use_mega = false;
+  size_t mega_smem = 0;
+  int mega_grid = 0;
+  DBuf bar;
   // frame graph
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_ok = false;
@@ -284,6 +292,64 @@ static void frame_body(q3_session* s) {
   launch_sampler(s, 1);
 }
 
+// ---- persistent frame kernel ----------------------------------------------------------------------------
+static MegaArgs mega_args(q3_session* s) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  MegaArgs a{};
+  a.tk = {m->tl_dev, d.layers, d.hidden, d.inter, d.heads, d.kv_heads};
+  a.cp = {m->cl_dev, d.cp_layers, d.cp_hidden, d.cp_inter, d.cp_heads, d.cp_kv_heads};
+  a.codec_emb = m->codec_emb; a.t_norm = m->t_norm; a.codec_head = m->codec_head;
+  a.cp_proj_w = m->cp_proj_w; a.cp_proj_b = m->cp_proj_b; a.cp_norm = m->cp_norm;
+  for (int i = 0; i < 15; ++i) { a.cp_emb[i] = m->cp_emb[i]; a.cp_head[i] = m->cp_head[i]; }
+  a.cp_cos = m->cp_cos; a.cp_sin = m->cp_sin; a.t_cos = s->cos_tab.as<bf16>(); a.t_sin = s->sin_tab.as<bf16>();
+  a.H = d.hidden; a.C = d.cp_hidden; a.V = d.codec_vocab; a.cpV = d.cp_vocab; a.n_ac = d.groups - 1; a.B = s->B;
+  a.eps = d.rms_eps;
+  a.fs = s->fs;
+  a.tk_k = s->tk_k.as<bf16>(); a.tk_v = s->tk_v.as<bf16>(); a.cp_k = s->cp_k.as<bf16>(); a.cp_v = s->cp_v.as<bf16>();
+  a.max_seq = s->max_seq; a.cp_max_seq = d.cp_max_seq;
+  a.x = s->sc.x.as<bf16>(); a.qkv = s->sc.qkv.as<bf16>(); a.attn = s->sc.attn.as<bf16>(); a.o = s->sc.o.as<bf16>();
+  a.h1 = s->sc.h1.as<bf16>(); a.act = s->sc.act.as<bf16>(); a.step_input = s->step_input.as<bf16>();
+  a.logits = s->logits.as<float>();
+  a.bar = s->bar.as<unsigned>();
+  SampleArgs sa = make_sample_args(s->cfg, d.codec_vocab, s->B);
+  sa.logits = s->logits.as<float>();
+  sa.seen = s->fs.seen; sa.rng = s->fs.rng; sa.tok_out = s->fs.cur_tok; sa.token_count = s->fs.token_count;
+  sa.done = s->fs.done; sa.offset = s->fs.offset; sa.frame_idx = s->fs.frame_idx; sa.host_flags = nullptr; sa.advance = 1;
+  a.smp = sa;
+  return a;
+}
+
+static void mega_launch(q3_session* s, MegaArgs& a) {
+  Q3_CHECK_CUDA(cudaMemsetAsync(s->bar.p, 0, 4, s->st));
+  void* params[] = {(void*)&a};
+  Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega_kernel, dim3(s->mega_grid), dim3(MEGA_THREADS), params,
+                                            s->mega_smem, s->st));
+  Q3_COUNT_LAUNCH();
+}
+
+static void run_frames_mega(q3_session* s, int n) {
+  const int per_launch = 16;
+  int done_frames = 0, blk = 0;
+  bool stop = false;
+  while (done_frames < n && !stop) {
+    const int todo = std::min(per_launch, n - done_frames);
+    MegaArgs a = mega_args(s);
+    a.n_frames = todo; a.do_cp = a.do_finish = a.do_talker = a.do_sample = 1;
+    mega_launch(s, a);
+    done_frames += todo;
+    count_active_kernel<<<1, 32, 0, s->st>>>(s->fs.done, s->B, s->host_flags_dev + (blk & 1));
+    Q3_COUNT_LAUNCH();
+    Q3_CHECK_CUDA(cudaEventRecord(s->ev_poll[blk & 1], s->st));
+    if (blk > 0) {
+      Q3_CHECK_CUDA(cudaEventSynchronize(s->ev_poll[(blk - 1) & 1]));
+      if (s->host_flags[(blk - 1) & 1] == 0) stop = true;
+    }
+    ++blk;
+  }
+  s->frames_run += done_frames;
+}
+
 static void run_frames(q3_session* s, int n) {
   if (n <= 0) return;
   // KV overflow check (kv_cache.rs:293-300)
@@ -292,6 +358,10 @@ static void run_frames(q3_session* s, int n) {
   if (max_len + s->frames_run + n > s->max_seq)
     throw Q3Error(Q3_ERR_KV_OVERFLOW, "KV cache overflow: current=" + std::to_string(max_len + s->frames_run) +
                                           " + new=" + std::to_string(n) + " > max=" + std::to_string(s->max_seq));
+  if (s->use_mega) {
+    run_frames_mega(s, n);
+    return;
+  }
   int done_frames = 0;
   uint64_t per_frame = 0;
   if (!s->graph_ok) {
@@ -542,6 +612,17 @@ q3_status q3_model_finalize(q3_model* m) {
     }
     build_stack(m, cp + ".model", m->cdims(), m->cl);
     m->cp_norm = needb(m, cp + ".model.norm.weight");
+    {
+      DBuf t1, t2;
+      t1.alloc(m->tl.size() * sizeof(LayerW));
+      t2.alloc(m->cl.size() * sizeof(LayerW));
+      Q3_CHECK_CUDA(cudaMemcpy(t1.p, m->tl.data(), m->tl.size() * sizeof(LayerW), cudaMemcpyHostToDevice));
+      Q3_CHECK_CUDA(cudaMemcpy(t2.p, m->cl.data(), m->cl.size() * sizeof(LayerW), cudaMemcpyHostToDevice));
+      m->tl_dev = t1.as<LayerW>();
+      m->cl_dev = t2.as<LayerW>();
+      m->owned.push_back(std::move(t1));
+      m->owned.push_back(std::move(t2));
+    }
     DBuf c, s;
     build_rope_table(d.cp_rope_positions, d.rope_theta, c, s);
     m->cp_cos = c.as<bf16>();
@@ -620,6 +701,24 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
   if (attn_smem_bytes(max_seq) > 48 * 1024)
     Q3_CHECK_CUDA(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)attn_smem_bytes(max_seq)));
+  {
+    // persistent frame kernel: batch <= 8 (16 tokens in the CP prefill pass), needs one resident CTA per SM
+    const char* env = std::getenv("Q3_MEGA");
+    const bool want = !(env && env[0] == '0');
+    s->mega_smem = mega_smem_bytes(d, B, max_seq);
+    s->bar.alloc(64);
+    s->bar.zero();
+    if (want && 2 * B <= MEGA_TMAX && s->mega_smem <= 227 * 1024 && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 &&
+        d.inter % 32 == 0 && d.cp_inter % 32 == 0 && d.codec_vocab % 16 == 0 && d.cp_vocab % 16 == 0) {
+      Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->mega_smem));
+      int per_sm = 0;
+      Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_frames_mega_kernel, MEGA_THREADS, s->mega_smem));
+      if (per_sm >= 1) {
+        s->use_mega = true;
+        s->mega_grid = m->num_sms;
+      }
+    }
+  }
   FrameState& fs = s->fs;
   fs.cur_tok = s->cur_tok.as<uint32_t>(); fs.done = s->done.as<int>(); fs.n_frames = s->n_frames.as<int>();
   fs.token_count = s->token_count.as<int>(); fs.offset = s->offset.as<int>(); fs.frame_idx = s->frame_idx.as<int>();
@@ -944,10 +1043,17 @@ q3_status q3_talker_step(q3_session* s, const uint16_t* step_input, uint16_t* hi
                                           " + new=1 > max=" + std::to_string(s->max_seq));
   ensure_scratch(s, 2 * s->B);
   bf16* x = s->sc.x.as<bf16>();
-  Q3_CHECK_CUDA(cudaMemcpyAsync(x, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
-  layers_forward(s, s->m->tl, s->m->tdims(), x, s->B, 1, s->fs.offset, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq,
-                 s->cos_tab.as<bf16>(), s->sin_tab.as<bf16>());
-  talker_head(s, x, d.hidden);
+  if (s->use_mega) {
+    Q3_CHECK_CUDA(cudaMemcpyAsync(s->step_input.p, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
+    MegaArgs a = mega_args(s);
+    a.n_frames = 1; a.do_talker = 1; a.ext_step_input = s->step_input.as<bf16>();
+    mega_launch(s, a);
+  } else {
+    Q3_CHECK_CUDA(cudaMemcpyAsync(x, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
+    layers_forward(s, s->m->tl, s->m->tdims(), x, s->B, 1, s->fs.offset, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq,
+                   s->cos_tab.as<bf16>(), s->sin_tab.as<bf16>());
+    talker_head(s, x, d.hidden);
+  }
   add_int_kernel<<<1, 256, 0, s->st>>>(s->fs.offset, s->B, 1);
   Q3_COUNT_LAUNCH();
   s->frames_run += 1;
@@ -968,7 +1074,14 @@ q3_status q3_code_predictor_frame(q3_session* s, const uint16_t* last_hidden, co
   Q3_CHECK_CUDA(cudaMemcpyAsync(s->last_hidden.p, last_hidden, (size_t)B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
   Q3_CHECK_CUDA(cudaMemcpyAsync(s->cur_tok.p, sem_tokens, B * 4, cudaMemcpyHostToDevice, s->st));
   if (logits_out) s->cp_logits.ensure((size_t)n_ac * B * d.cp_vocab * 4);
-  cp_frame(s, logits_out ? s->cp_logits.as<float>() : nullptr);
+  if (s->use_mega) {
+    ensure_scratch(s, 2 * B);
+    MegaArgs a = mega_args(s);
+    a.n_frames = 1; a.do_cp = 1; a.cp_logits = logits_out ? s->cp_logits.as<float>() : nullptr;
+    mega_launch(s, a);
+  } else {
+    cp_frame(s, logits_out ? s->cp_logits.as<float>() : nullptr);
+  }
   std::vector<unsigned long long> keys((size_t)n_ac * B);
   Q3_CHECK_CUDA(cudaMemcpyAsync(keys.data(), s->amax.p, keys.size() * 8, cudaMemcpyDeviceToHost, s->st));
   std::vector<float> lg;
