@@ -322,8 +322,8 @@ __device__ __forceinline__ void frame_finish_row(const FrameState& st, const Emb
   if (threadIdx.x < 16) {
     uint32_t c;
     if (threadIdx.x == 0) c = st.cur_tok[b];
-    else if (threadIdx.x < n_ac) c = st.frame_codes[b * 16 + threadIdx.x];
-    else c = argmax_key_index(st.amax[(size_t)(n_ac - 1) * B + b]);
+    else if (threadIdx.x < n_ac) c = __ldcg(st.frame_codes + b * 16 + threadIdx.x);
+    else c = argmax_key_index(__ldcg(st.amax + (size_t)(n_ac - 1) * B + b));
     codes_sm[threadIdx.x] = c;
   }
   __syncthreads();
@@ -451,7 +451,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
   for (int i = tid; i < 4096; i += NT) {
     float x = -INFINITY;
     if (i < V) {
-      x = lg[i];
+      x = __ldcg(lg + i);
       if (a.use_pen && seen[i]) x = x * ((x > 0.f) ? a.inv_pen : a.pen);          // sampling.rs:388-399
       if (i >= V - 1024 && i != Q3_CODEC_EOS) x = -INFINITY;                      // tts.rs:26-37 (constant EOS id, lib.rs:543-547)
       if (a.eos >= 0 && tcount < a.min_new_tokens && i == a.eos) x = -INFINITY;   // lib.rs:1304-1318

@@ -31,6 +31,8 @@
 constexpr int MEGA_THREADS = 512;
 constexpr int MEGA_WARPS = 16;
 constexpr int MEGA_TMAX = 16;       // tokens per phase (batch <= 8: the CP prefill pass has 2 tokens per row)
+constexpr int MEGA_MAX_TILES = 4;   // 16-row tiles per CTA per phase (N <= 4 * 16 * gridDim.x rows per matrix)
+constexpr int MEGA_MAX_OUT = (MEGA_MAX_TILES * 16 * MEGA_TMAX + 511) / 512;   // outputs per thread in the combine
 
 struct MegaStack { const LayerW* layers; int n_layers, H, I, heads, kv_heads; };
 
@@ -49,26 +51,58 @@ struct MegaArgs {
   float* logits;
   float* cp_logits;      // optional [n_ac][B][cpV]
   unsigned* bar;
+  float *ssA, *ssB;      // per-CTA partial sums of squares [G][MEGA_TMAX] (post-attention sum / layer output)
   SampleArgs smp;
   int n_frames;          // loop iterations to run in this launch
   int do_cp, do_finish, do_talker, do_sample;
   const bf16* ext_step_input;   // per-op entry: talker input supplied by the caller (do_finish == 0)
+  unsigned long long* prof;     // optional: %globaltimer stamps of block 0 (tools/profile_mega.py)
+  int prof_cap;
+  int bar_mode;                 // 0: release-reduction + acquire spin; 1: fence + atomic + volatile spin
+  int prefetch_mode;            // 0: none, 1: own rows at phase start, 2: own + next phase's rows
+  int bench_barriers;           // > 0: run only this many grid barriers (micro-benchmark)
+  int dbg;                      // timing experiments only: 1 skip weight loads, 2 skip X loads, 4 skip combine, 8 skip MMA
 };
+
+__device__ unsigned int g_prof_idx;
+__shared__ unsigned int s_prof_idx;
+__device__ __forceinline__ void prof_stamp(const MegaArgs& a, int tag) {
+  if (a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned i = s_prof_idx++;
+    if ((int)i < a.prof_cap) a.prof[i] = (t << 8) | (unsigned long long)(tag & 0xff);
+    g_prof_idx = i + 1;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 struct GridBar {
   unsigned* ctr;
   unsigned epoch;
+  int mode;
 };
+// Grid-wide barrier on a monotonically increasing counter (zeroed by the host before every launch; the
+// launch is cooperative so all CTAs are resident).  Thread 0 publishes the CTA's writes with a release
+// reduction and waits with acquire loads; bar.sync extends both to the rest of the CTA.  Data produced by
+// OTHER CTAs is always read with ld.global.cg (L2), so a stale L1 line can never be observed.
 __device__ __forceinline__ void grid_sync(GridBar& gb) {
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned target = (gb.epoch + 1u) * gridDim.x;
-    __threadfence();
-    atomicAdd(gb.ctr, 1u);
-    while (*((volatile unsigned*)gb.ctr) < target) {
+    if (gb.mode == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      } while (v < target);
+    } else {
+      __threadfence();
+      atomicAdd(gb.ctr, 1u);
+      while (*((volatile unsigned*)gb.ctr) < target) {
+      }
+      __threadfence();
     }
-    __threadfence();
   }
   gb.epoch += 1u;
   __syncthreads();
@@ -87,20 +121,20 @@ __device__ __forceinline__ void mma_bf16_16816(float c[4], uint32_t a0, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------------
-// activation staging
-enum XMode { X_PLAIN = 0, X_RMSNORM = 1, X_RESNORM = 2, X_CP0 = 3, X_CPG = 4 };
+// skinny-GEMM phase descriptor
+enum XMode { X_PLAIN = 0, X_NORM = 1, X_CP0 = 3, X_CPG = 4 };
+enum MegaEpi { EPI_O_H1 = 16 };     // o_proj: h1 = bf16(bf16(acc) + x) -> Y, partial sum of squares of the unrounded sum
 
 struct GemvP {
   const bf16* W;
   const bf16* W2;        // dual (SwiGLU) partner or null
   int N, K, T;
   int xmode;
-  const bf16* X;         // X_PLAIN / X_RMSNORM: [T][ldx];  X_RESNORM: the o_proj output
+  const bf16* X;         // [T][ldx]
   int ldx;
-  const bf16* X2;        // X_RESNORM: residual input x
-  const bf16* norm_w;
-  bf16* h1_out;          // X_RESNORM: rounded sum written by CTA 0
-  bf16* xn_out;          // X_RMSNORM: normalised rows written by CTA 0 (talker last_hidden)
+  const bf16* norm_w;    // X_NORM
+  const float* ss_in;    // X_NORM: per-CTA partial sums of squares [G][MEGA_TMAX] of the rows of X, or null (computed here)
+  bf16* xn_out;          // X_NORM: normalised rows written by CTA 0 (talker last_hidden)
   const bf16* emb;       // X_CP0: talker codec embedding; X_CPG: codec_embeddings[g-1]
   int g;                 // X_CPG: pass index
   int epi;
@@ -111,219 +145,298 @@ struct GemvP {
   int ldr;
   float* Yf;
   unsigned long long* amax;
+  float* ss_out;         // partial sums of squares of the values written to Y, [G][MEGA_TMAX], or null
+  // weights of the NEXT skinny-GEMM phase: pulled into L2 while this phase runs (they do not depend on
+  // activations), so HBM keeps streaming across the grid barrier.
+  const bf16* next_W;
+  const bf16* next_W2;
+  int next_N, next_K;
 };
 
-// xs: [T8][K + 32] bf16, rows >= T zero.  Returns nothing; ends with __syncthreads().
-__device__ __noinline__ void mega_stage_x(const MegaArgs& a, const GemvP& p, bf16* xs, float* s_part) {
-  const int K = p.K, XS = K + 32, T = p.T, T8 = (T + 7) & ~7;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const bool writer = blockIdx.x == 0;
-  auto src_row = [&](int t) -> const bf16* {
-    if (p.xmode == X_CP0) {
-      const int b = t >> 1;
-      return (t & 1) ? p.emb + (size_t)a.fs.cur_tok[b] * K : a.fs.last_hidden + (size_t)b * K;
-    }
-    if (p.xmode == X_CPG) {
-      const uint32_t code = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + t));
-      return p.emb + (size_t)code * K;
-    }
-    return p.X + (size_t)t * p.ldx;
-  };
-  if (p.xmode == X_CPG && writer && tid < T)
-    a.fs.frame_codes[tid * 16 + p.g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + tid));
-  if (p.xmode == X_CP0 && writer && tid < a.B) a.fs.frame_codes[tid * 16] = a.fs.cur_tok[tid];
-  // zero padding rows
-  for (int i = tid; i < (T8 - T) * (K >> 3); i += MEGA_THREADS) {
-    int r = i / (K >> 3), q = i - r * (K >> 3);
-    *reinterpret_cast<uint4*>(xs + (size_t)(T + r) * XS + q * 8) = make_uint4(0, 0, 0, 0);
+// Contiguous 8-row units dealt evenly to the CTAs: CTA c owns rows [r0, r1).
+__device__ __forceinline__ void mega_row_range(int N, int& r0, int& r1) {
+  const int units = N >> 3, G = gridDim.x, c = blockIdx.x;
+  const int base = units / G, rem = units - base * G;
+  const int u0 = c * base + min(c, rem);
+  r0 = u0 << 3;
+  r1 = (u0 + base + (c < rem ? 1 : 0)) << 3;
+}
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, size_t bytes) {
+  // cp.async.bulk.prefetch: one instruction pulls a contiguous range into L2 (TMA engine, no registers held)
+  while (bytes > 0) {
+    const unsigned chunk = (unsigned)(bytes > (size_t)(1u << 20) ? (1u << 20) : bytes);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(chunk) : "memory");
+    p = reinterpret_cast<const char*>(p) + chunk;
+    bytes -= chunk;
   }
-  if (p.xmode == X_PLAIN || p.xmode == X_CP0 || p.xmode == X_CPG) {
-    const int K8 = K >> 3;
-    for (int i = tid; i < T * K8; i += MEGA_THREADS) {
-      int t = i / K8, q = i - t * K8;
-      *reinterpret_cast<uint4*>(xs + (size_t)t * XS + q * 8) = ldcg16(src_row(t) + q * 8);
-    }
-    __syncthreads();
-    return;
-  }
-  const bool res = p.xmode == X_RESNORM;
-  if (K >= 1024) {
-    const int grp = tid >> 7, g = tid & 127;      // four 128-thread groups, one token each
-    for (int t = grp; t < T; t += 4) {
-      const bf16* xr = p.X + (size_t)t * p.ldx;
-      const bf16* rr = res ? p.X2 + (size_t)t * p.ldx : nullptr;
-      float pp[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pp[e] = 0.f;
-      for (int c = 8 * g; c < K; c += 1024) {
-        float f[8];
-        unpack8(ldcg16(xr + c), f);
-        if (res) {
-          float r2[8];
-          unpack8(ldcg16(rr + c), r2);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = f[e] + r2[e];
-          // keep the ROUNDED sum in shared memory for pass 2 (the reference re-reads its stored sum)
-          uint4 pk = pack8(f);
-          *reinterpret_cast<uint4*>(xs + (size_t)t * XS + c) = pk;
-          if (writer) *reinterpret_cast<uint4*>(p.h1_out + (size_t)t * K + c) = pk;
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) pp[e] = fmaf(f[e], f[e], pp[e]);
-      }
-      const float tot = sumsq_ref_large_finish(pp, g, s_part + grp * 32, 1 + grp);
-      const float sc = ref_mean_rsqrt(tot, K, a.eps);
-      for (int c = 8 * g; c < K; c += 1024) {
-        float f[8], w[8], o[8];
-        if (res) unpack8(*reinterpret_cast<const uint4*>(xs + (size_t)t * XS + c), f);
-        else unpack8(ldcg16(xr + c), f);
-        unpack8(*reinterpret_cast<const uint4*>(p.norm_w + c), w);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = (sc * f[e]) * w[e];
-        const uint4 pk = pack8(o);
-        *reinterpret_cast<uint4*>(xs + (size_t)t * XS + c) = pk;
-        if (p.xn_out != nullptr && writer) *reinterpret_cast<uint4*>(p.xn_out + (size_t)t * K + c) = pk;
-      }
-    }
-  } else {
-    for (int t = warp; t < T; t += MEGA_WARPS) {
-      const bf16* xr = p.X + (size_t)t * p.ldx;
-      const bf16* rr = res ? p.X2 + (size_t)t * p.ldx : nullptr;
-      float tmp = 0.f;
-      for (int c = lane; c < K; c += 32) {
-        float v = ldcg_bf16(xr + c);
-        if (res) {
-          v = v + ldcg_bf16(rr + c);
-          const bf16 rounded = f2bf(v);
-          xs[(size_t)t * XS + c] = rounded;
-          if (writer) p.h1_out[(size_t)t * K + c] = rounded;
-        }
-        tmp = fmaf(v, v, tmp);
-      }
-      tmp = warp_sum_xor(tmp);
-      const float sc = ref_mean_rsqrt(tmp, K, a.eps);
-      for (int c = lane; c < K; c += 32) {
-        const float f = res ? bf2f(xs[(size_t)t * XS + c]) : ldcg_bf16(xr + c);
-        const bf16 o = f2bf((sc * f) * bf2f(p.norm_w[c]));
-        xs[(size_t)t * XS + c] = o;
-        if (p.xn_out != nullptr && writer) p.xn_out[(size_t)t * K + c] = o;
-      }
-    }
-  }
-  __syncthreads();
+}
+__device__ __forceinline__ void mega_prefetch_rows(const bf16* W, const bf16* W2, int N, int K) {
+  if (W == nullptr || threadIdx.x != 0) return;
+  int r0, r1;
+  mega_row_range(N, r0, r1);
+  if (r1 <= r0) return;
+  l2_prefetch_bulk(W + (size_t)r0 * K, (size_t)(r1 - r0) * K * 2);
+  if (W2 != nullptr) l2_prefetch_bulk(W2 + (size_t)r0 * K, (size_t)(r1 - r0) * K * 2);
 }
 
 // ---------------------------------------------------------------------------------------------------
-// One skinny-GEMM phase.  smem: xs [T8][K+32] bf16 | red [16 warps][NT][(DUAL?2:1)][16][8] f32
-template <bool DUAL>
-__device__ __noinline__ void mega_gemv(const MegaArgs& a, const GemvP& p, unsigned char* smem, float* s_part) {
-  const int K = p.K, XS = K + 32, T = p.T, T8 = (T + 7) & ~7, NT = T8 >> 3;
-  bf16* xs = reinterpret_cast<bf16*>(smem);
-  float* red = reinterpret_cast<float*>(smem + (((size_t)T8 * XS * 2 + 127) & ~(size_t)127));
-  // 16-row tiles; 8-row tiles when there would be fewer tiles than CTAs
-  const int RT = (p.N / 16 >= (int)gridDim.x) ? 16 : 8;
-  const int n_tiles = p.N / RT;
-  if ((int)blockIdx.x >= n_tiles) return;          // nothing to do here (block 0 always has a tile)
-  mega_stage_x(a, p, xs, s_part);
+// One skinny-GEMM phase.  No activation staging: every warp loads the B fragments of ITS k-slices straight
+// from L2 (ld.global.cg, 16 B per lane) next to its weight loads, and applies the RMSNorm prologue
+// xn = bf16((scale_t * x) * w_k) on the fly.  scale_t comes from per-CTA partial sums of squares that the
+// PRODUCING phase left in `ss_in` (summed here in a fixed order -> deterministic), so no CTA ever re-reads
+// whole activation rows.  The phase is instruction-issue bound at these sizes (16 warps x ~10^3 instructions
+// per phase was 2 us of pure issue time), so the body is specialised at compile time on (DUAL, NT, NORM) and
+// keeps integer divisions and predicated zero-fills off the common path.
+// smem: scale[16] | sqbuf [64 rows][16] | red [tile][16 warps][NT][NM][16][8] f32
+template <bool DUAL, int NT, bool NORM>
+__device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsigned char* smem) {
+  float* scale_s = reinterpret_cast<float*>(smem);
+  float* sqbuf = scale_s + MEGA_TMAX;                       // [MEGA_MAX_TILES*16 rows][MEGA_TMAX] squares for ss_out
+  float* red = sqbuf + MEGA_MAX_TILES * 16 * MEGA_TMAX;     // partial sums
+  const int K = p.K, T = p.T;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
-  const int ksteps = K >> 5;                       // 32 k per step
+  int r0, r1;
+  mega_row_range(p.N, r0, r1);
+  if (r1 <= r0) {                                    // no rows here (block 0 always owns rows)
+    if (p.ss_out != nullptr && tid < MEGA_TMAX) p.ss_out[blockIdx.x * MEGA_TMAX + tid] = 0.f;
+    if (a.prefetch_mode >= 2) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+    return;
+  }
+  if (a.prefetch_mode >= 1) mega_prefetch_rows(p.W, p.W2, p.N, K);
+  prof_stamp(a, 1);
+  if (NORM) {
+    // row scales: one warp per token
+    for (int t = warp; t < T; t += MEGA_WARPS) {
+      float tot = 0.f;
+      if (p.ss_in != nullptr) {
+        for (int c = lane; c < (int)gridDim.x; c += 32) tot += __ldcg(p.ss_in + c * MEGA_TMAX + t);
+      } else {
+        const bf16* xr = p.X + (size_t)t * p.ldx;
+        for (int c = 8 * lane; c < K; c += 256) {
+          float f[8];
+          unpack8(ldcg16(xr + c), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot = fmaf(f[e], f[e], tot);
+        }
+      }
+      tot = warp_sum_xor(tot);
+      if (lane == 0) scale_s[t] = ref_mean_rsqrt(tot, K, a.eps);
+    }
+    __syncthreads();
+  }
+  prof_stamp(a, 2);
+  // this lane's activation rows: token nt*8 + g of each n-tile
+  const bf16* xrow[NT];
+  float xsc[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int t = nt * 8 + g;
+    xrow[nt] = nullptr;
+    xsc[nt] = 0.f;
+    if (t < T) {
+      if (p.xmode == X_CP0) {
+        const int b = t >> 1;
+        xrow[nt] = (t & 1) ? p.emb + (size_t)__ldcg(a.fs.cur_tok + b) * K : a.fs.last_hidden + (size_t)b * K;
+      } else if (p.xmode == X_CPG) {
+        xrow[nt] = p.emb + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + t)) * K;
+      } else {
+        xrow[nt] = p.X + (size_t)t * p.ldx;
+      }
+      if (NORM) xsc[nt] = scale_s[t];
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (p.xmode == X_CPG && tid < T)
+      a.fs.frame_codes[tid * 16 + p.g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + tid));
+    if (p.xmode == X_CP0 && tid < a.B) a.fs.frame_codes[tid * 16] = __ldcg(a.fs.cur_tok + tid);
+  }
+  const bool write_xn = NORM && p.xn_out != nullptr && blockIdx.x == 0;
+  const int ksteps = K >> 5;                         // 32 k per step; warp w owns k-steps w, w+16, w+32, ...
   constexpr int NM = DUAL ? 2 : 1;
-  constexpr int U = DUAL ? 2 : 4;                  // k-steps loaded per batch
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int n0 = tile * RT;
-    float acc[NM][2][4];                           // [matrix][n-tile][frag]  (T8 <= 16 -> NT <= 2)
+  constexpr int JU = 2;                              // k-steps per chunk: all loads of a chunk are issued back to back
+  const int jn = ksteps > warp ? (ksteps - warp + MEGA_WARPS - 1) / MEGA_WARPS : 0;   // this warp's k-steps
+  const int n_chunks = max(1, ((ksteps + MEGA_WARPS - 1) / MEGA_WARPS + JU - 1) / JU);   // uniform over warps
+  const int n_tiles = (r1 - r0 + 15) >> 4;
+  const int koff0 = warp * 32 + 8 * tg;              // element offset of this lane inside its first k-step
+  const bool k_full = (ksteps % (MEGA_WARPS * JU)) == 0;   // every chunk of every warp is complete (all real models)
+
+  // residual inputs of the epilogue, fetched now so their L2 latency hides behind the weight stream.
+  // Combine mapping: output idx = tid + it*512 -> token t = idx >> 6, CTA-local row = idx & 63.
+  float rpre[MEGA_MAX_OUT];
+#pragma unroll
+  for (int it = 0; it < MEGA_MAX_OUT; ++it) {
+    rpre[it] = 0.f;
+    const int idx = tid + it * MEGA_THREADS;
+    const int t = idx >> 6, n = r0 + (idx & 63);
+    if ((p.epi == EPI_RESIDUAL || p.epi == EPI_O_H1) && t < T && n < r1) rpre[it] = ldcg_bf16(p.R + (size_t)t * p.ldr + n);
+  }
+
+  uint4 wl[NM][JU], wh[NM][JU], xv[NT][JU], wn[JU];
+  auto load_chunk = [&](int tile, int c) {
+    const int n0 = r0 + (tile << 4);
+    const bool hi_ok = (n0 + 8) < r1;
+    const size_t woff = (size_t)(n0 + g) * K + koff0 + (size_t)c * (JU * 512);
+    const int xo = koff0 + c * (JU * 512);
+    if (k_full && hi_ok) {                           // common path: no predication, no zero fill
+#pragma unroll
+      for (int u = 0; u < JU; ++u) {
+        wl[0][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W + woff + u * 512));
+        wh[0][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W + woff + (size_t)8 * K + u * 512));
+        if (DUAL) {
+          wl[NM - 1][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W2 + woff + u * 512));
+          wh[NM - 1][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W2 + woff + (size_t)8 * K + u * 512));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < JU; ++u) {
+        const bool ok = (c * JU + u) < jn;
+        wl[0][u] = make_uint4(0, 0, 0, 0);
+        wh[0][u] = make_uint4(0, 0, 0, 0);
+        if (DUAL) { wl[NM - 1][u] = make_uint4(0, 0, 0, 0); wh[NM - 1][u] = make_uint4(0, 0, 0, 0); }
+        if (ok) {
+          wl[0][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W + woff + u * 512));
+          if (hi_ok) wh[0][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W + woff + (size_t)8 * K + u * 512));
+          if (DUAL) {
+            wl[NM - 1][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W2 + woff + u * 512));
+            if (hi_ok) wh[NM - 1][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W2 + woff + (size_t)8 * K + u * 512));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < JU; ++u) {
+      const bool ok = k_full || (c * JU + u) < jn;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        xv[nt][u] = make_uint4(0, 0, 0, 0);
+        if (ok && xrow[nt] != nullptr) xv[nt][u] = ldcg16(xrow[nt] + xo + u * 512);
+      }
+      if (NORM) {
+        wn[u] = make_uint4(0, 0, 0, 0);
+        if (ok) wn[u] = *reinterpret_cast<const uint4*>(p.norm_w + xo + u * 512);
+      }
+    }
+  };
+  float acc[NM][NT][4];
+  load_chunk(0, 0);
+  for (int tile = 0; tile < n_tiles; ++tile) {
 #pragma unroll
     for (int m = 0; m < NM; ++m)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
-    const bf16* wlo[NM];
-    const bf16* whi[NM];
-    wlo[0] = p.W + (size_t)(n0 + g) * K + 8 * tg;
-    whi[0] = p.W + (size_t)(n0 + g + 8) * K + 8 * tg;
-    if (DUAL) {
-      wlo[1] = p.W2 + (size_t)(n0 + g) * K + 8 * tg;
-      whi[1] = p.W2 + (size_t)(n0 + g + 8) * K + 8 * tg;
-    }
-    for (int ks0 = warp; ks0 < ksteps; ks0 += MEGA_WARPS * U) {
-      uint4 wl[NM][U], wh[NM][U];
+    for (int c = 0; c < n_chunks; ++c) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ks = ks0 + u * MEGA_WARPS;
-        if (ks < ksteps) {
+      for (int u = 0; u < JU; ++u) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint4 x4 = xv[nt][u];
+          if (NORM) {
+            float f[8], w[8];
+            unpack8(x4, f);
+            unpack8(wn[u], w);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = (xsc[nt] * f[e]) * w[e];
+            x4 = pack8(f);
+            if (write_xn && tile == 0 && xrow[nt] != nullptr && (c * JU + u) < jn)
+              *reinterpret_cast<uint4*>(p.xn_out + (size_t)(nt * 8 + g) * K + koff0 + (c * JU + u) * 512) = x4;
+          }
 #pragma unroll
           for (int m = 0; m < NM; ++m) {
-            wl[m][u] = ldg_stream(reinterpret_cast<const uint4*>(wlo[m] + ks * 32));
-            if (RT == 16) wh[m][u] = ldg_stream(reinterpret_cast<const uint4*>(whi[m] + ks * 32));
-            else wh[m][u] = make_uint4(0, 0, 0, 0);
+            mma_bf16_16816(acc[m][nt], wl[m][u].x, wh[m][u].x, wl[m][u].y, wh[m][u].y, x4.x, x4.y);
+            mma_bf16_16816(acc[m][nt], wl[m][u].z, wh[m][u].z, wl[m][u].w, wh[m][u].w, x4.z, x4.w);
           }
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int ks = ks0 + u * MEGA_WARPS;
-        if (ks < ksteps) {
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt) {
-            if (nt < NT) {
-              const uint4 xv = *reinterpret_cast<const uint4*>(xs + (size_t)(nt * 8 + g) * XS + ks * 32 + 8 * tg);
-#pragma unroll
-              for (int m = 0; m < NM; ++m) {
-                mma_bf16_16816(acc[m][nt], wl[m][u].x, wh[m][u].x, wl[m][u].y, wh[m][u].y, xv.x, xv.y);
-                mma_bf16_16816(acc[m][nt], wl[m][u].z, wh[m][u].z, wl[m][u].w, wh[m][u].w, xv.z, xv.w);
-              }
-            }
-          }
-        }
-      }
+      // the registers are free again: put the next chunk (possibly of the next tile) in flight right away, so it
+      // overlaps the cross-warp combine below
+      if (c + 1 < n_chunks) load_chunk(tile, c + 1);
+      else if (tile + 1 < n_tiles) load_chunk(tile + 1, 0);
     }
-    // partial sums -> shared memory: red[warp][nt][m][row 16][col 8]
+    // this tile's partial sums -> shared memory (combined for all tiles at once below)
 #pragma unroll
     for (int m = 0; m < NM; ++m)
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-        if (nt < NT) {
-          float* r = red + ((((size_t)warp * NT + nt) * NM + m) * 16) * 8;
-          r[g * 8 + 2 * tg] = acc[m][nt][0];
-          r[g * 8 + 2 * tg + 1] = acc[m][nt][1];
-          r[(g + 8) * 8 + 2 * tg] = acc[m][nt][2];
-          r[(g + 8) * 8 + 2 * tg + 1] = acc[m][nt][3];
-        }
-    __syncthreads();
-    // fixed-order combine + epilogue: thread -> (row, token)
-    for (int idx = tid; idx < RT * T; idx += MEGA_THREADS) {
-      const int row = idx % RT, t = idx / RT, nt = t >> 3, col = t & 7;
+      for (int nt = 0; nt < NT; ++nt) {
+        float* r = red + (((((size_t)tile * MEGA_WARPS + warp) * NT + nt) * NM + m) * 16) * 8;
+        *reinterpret_cast<float2*>(r + g * 8 + 2 * tg) = make_float2(acc[m][nt][0], acc[m][nt][1]);
+        *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * tg) = make_float2(acc[m][nt][2], acc[m][nt][3]);
+      }
+  }
+  __syncthreads();
+  // ---- fixed-order combine + epilogue for every (token, CTA-local row), spread over all 512 threads ----
+#pragma unroll
+  for (int it = 0; it < MEGA_MAX_OUT; ++it) {
+    const int idx = tid + it * MEGA_THREADS;
+    const int t = idx >> 6, rem = idx & 63, tile = rem >> 4, row = rem & 15;
+    const int n = r0 + rem, nt = t >> 3, col = t & 7;
+    const bool valid = t < T && n < r1;
+    float sq = 0.f;             // contribution to the partial sum of squares of what the NEXT norm will see
+    if (valid) {
       float v0 = 0.f, v1 = 0.f;
+      const float* rb = red + ((((size_t)tile * MEGA_WARPS) * NT + nt) * NM * 16 + row) * 8 + col;
 #pragma unroll
       for (int w = 0; w < MEGA_WARPS; ++w) {
-        v0 += red[((((size_t)w * NT + nt) * NM + 0) * 16 + row) * 8 + col];
-        if (DUAL) v1 += red[((((size_t)w * NT + nt) * NM + 1) * 16 + row) * 8 + col];
+        v0 += rb[(size_t)w * NT * NM * 128];
+        if (DUAL) v1 += rb[(size_t)w * NT * NM * 128 + 128];
       }
-      const int n = n0 + row;
       const float v = rbf(v0);
       switch (p.epi) {
         case EPI_STORE: p.Y[(size_t)t * p.ldy + n] = f2bf(v); break;
-        case EPI_BIAS: p.Y[(size_t)t * p.ldy + n] = f2bf(v + bf2f(p.bias[n])); break;
-        case EPI_BIAS_SILU: {
+        case EPI_BIAS: {
           const float y = rbf(v + bf2f(p.bias[n]));
-          p.Y[(size_t)t * p.ldy + n] = f2bf(silu_f(y));
+          p.Y[(size_t)t * p.ldy + n] = f2bf(y);
+          sq = y * y;
         } break;
         case EPI_RESIDUAL: {
-          const float r = ldcg_bf16(p.R + (size_t)t * p.ldr + n);
-          p.Y[(size_t)t * p.ldy + n] = f2bf(r + v);
+          const float y = rbf(rpre[it] + v);
+          p.Y[(size_t)t * p.ldy + n] = f2bf(y);
+          sq = y * y;             // the next layer's input_layernorm reads the stored (rounded) tensor
+        } break;
+        case EPI_O_H1: {
+          const float su = rpre[it] + v;                                     // x + attn_out, un-rounded f32
+          p.Y[(size_t)t * p.ldy + n] = f2bf(su);                            // h1: the rounded sum
+          sq = su * su;           // fused_residual_rmsnorm.cu:60-65: sum of squares of the UN-rounded sum
         } break;
         case EPI_SWIGLU: {
-          const float s = rbf(silu_f(v));
-          p.Y[(size_t)t * p.ldy + n] = f2bf(s * rbf(v1));
+          const float sg = rbf(silu_f(v));
+          p.Y[(size_t)t * p.ldy + n] = f2bf(sg * rbf(v1));
         } break;
         case EPI_LOGITS: {
           if (p.Yf != nullptr) p.Yf[(size_t)t * p.N + n] = v;
           if (p.amax != nullptr) atomicMax(p.amax + t, argmax_key(v, n));
         } break;
+        default: break;
       }
     }
+    if (p.ss_out != nullptr && t < MEGA_TMAX) sqbuf[rem * MEGA_TMAX + t] = sq;
+  }
+  if (p.ss_out != nullptr) {
     __syncthreads();
+    if (tid < MEGA_TMAX) {      // one thread per token sums its squares in a fixed order
+      float tot = 0.f;
+      if (tid < T)
+        for (int r = 0; r < n_tiles * 16; ++r) tot += sqbuf[r * MEGA_TMAX + tid];
+      p.ss_out[blockIdx.x * MEGA_TMAX + tid] = tot;
+    }
+  }
+  __syncthreads();
+  prof_stamp(a, 3);
+  if (a.prefetch_mode >= 2) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+}
+
+template <bool DUAL>
+__device__ __forceinline__ void mega_gemv(const MegaArgs& a, const GemvP& p, unsigned char* smem) {
+  const bool norm = p.xmode == X_NORM;
+  if (p.T <= 8) {
+    if (norm) mega_gemv_t<DUAL, 1, true>(a, p, smem);
+    else mega_gemv_t<DUAL, 1, false>(a, p, smem);
+  } else {
+    if (norm) mega_gemv_t<DUAL, 2, true>(a, p, smem);
+    else mega_gemv_t<DUAL, 2, false>(a, p, smem);
   }
 }
 
@@ -352,7 +465,7 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
     bf16* vbase = p.v_cache + ((size_t)b * p.kv_heads + kvh) * p.max_seq * 128;
     for (int s = 0; s < p.S; ++s) {
       const int t = b * p.S + s;
-      const int pos = (p.pos_base ? p.pos_base[b] : 0) + p.pos_add + s;
+      const int pos = (p.pos_base ? __ldcg(p.pos_base + b) : 0) + p.pos_add + s;
       const int L = pos + 1;
       // warps 0,1: q heads 2kvh, 2kvh+1; warp 2: k; warp 3: v
       if (warp < 4) {
@@ -449,39 +562,77 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Phase descriptors live in SHARED memory: thread 0 fills them, everybody reads them (broadcast).  Building
+// them per thread on the stack would cost ~150 B of local-memory traffic per thread per phase (6 GB of DRAM
+// writes per frame at 75 k threads x 546 phases -- measured with ncu before this change).
+struct MegaShared {
+  MegaArgs a;
+  GemvP gp;
+  AttnP ap;
+  uint32_t codes[16];
+};
+
+#define MEGA_FILL_BEGIN(sh) if (threadIdx.x == 0) { GemvP& q = (sh).gp; q = GemvP{};
+#define MEGA_FILL_END() } __syncthreads();
+
 // One decoder stack over T = B*S tokens, in place on a.x  (DecoderLayer::forward x layers).
-__device__ __noinline__ void mega_layers(const MegaArgs& a, const MegaStack& st, int T, int S, const int* pos_base, int pos_add, bf16* kc,
-                            bf16* vc, int cache_seq, const bf16* cos_tab, const bf16* sin_tab, unsigned char* smem,
-                            float* s_part, GridBar& gb) {
+__device__ __noinline__ void mega_layers(MegaShared& sh, const MegaStack& st, int T, int S, const int* pos_base, int pos_add,
+                                         bf16* kc, bf16* vc, int cache_seq, const bf16* cos_tab, const bf16* sin_tab,
+                                         unsigned char* smem, const float* first_ss, const bf16* after_W, int after_N,
+                                         int after_K, GridBar& gb) {
+  const MegaArgs& a = sh.a;
   const int nh = st.heads + 2 * st.kv_heads;
   const size_t layer_stride = (size_t)a.B * st.kv_heads * cache_seq * 128;
   for (int l = 0; l < st.n_layers; ++l) {
-    const LayerW w = st.layers[l];
-    GemvP q{};
-    q.W = w.wqkv; q.N = nh * 128; q.K = st.H; q.T = T; q.xmode = X_RMSNORM; q.X = a.x; q.ldx = st.H; q.norm_w = w.in_ln;
-    q.epi = EPI_STORE; q.Y = a.qkv; q.ldy = nh * 128;
-    mega_gemv<false>(a, q, smem, s_part);
+    const LayerW* wp = st.layers + l;
+    // P1: rms_norm(x) -> [q;k;v]
+    MEGA_FILL_BEGIN(sh)
+      q.W = wp->wqkv; q.N = nh * 128; q.K = st.H; q.T = T; q.xmode = X_NORM; q.X = a.x; q.ldx = st.H; q.norm_w = wp->in_ln;
+      q.ss_in = l == 0 ? first_ss : a.ssB;
+      q.epi = EPI_STORE; q.Y = a.qkv; q.ldy = nh * 128;
+      q.next_W = wp->wo; q.next_N = st.H; q.next_K = st.heads * 128;
+    MEGA_FILL_END()
+    mega_gemv<false>(a, sh.gp, smem);
     grid_sync(gb);
-    AttnP at{};
-    at.qkv = a.qkv; at.out = a.attn; at.k_cache = kc + l * layer_stride; at.v_cache = vc + l * layer_stride;
-    at.q_norm_w = w.q_norm; at.k_norm_w = w.k_norm; at.cos_tab = cos_tab; at.sin_tab = sin_tab; at.pos_base = pos_base;
-    at.pos_add = pos_add; at.S = S; at.B = a.B; at.heads = st.heads; at.kv_heads = st.kv_heads; at.max_seq = cache_seq;
-    mega_attn(a, at, smem);
+    // P2: QK-norm, RoPE, KV append, attention
+    if (threadIdx.x == 0) {
+      AttnP& at = sh.ap;
+      at.qkv = a.qkv; at.out = a.attn; at.k_cache = kc + l * layer_stride; at.v_cache = vc + l * layer_stride;
+      at.q_norm_w = wp->q_norm; at.k_norm_w = wp->k_norm; at.cos_tab = cos_tab; at.sin_tab = sin_tab; at.pos_base = pos_base;
+      at.pos_add = pos_add; at.S = S; at.B = a.B; at.heads = st.heads; at.kv_heads = st.kv_heads; at.max_seq = cache_seq;
+    }
+    __syncthreads();
+    prof_stamp(a, 4);
+    mega_attn(a, sh.ap, smem);
+    prof_stamp(a, 5);
     grid_sync(gb);
-    GemvP o{};
-    o.W = w.wo; o.N = st.H; o.K = st.heads * 128; o.T = T; o.xmode = X_PLAIN; o.X = a.attn; o.ldx = st.heads * 128;
-    o.epi = EPI_STORE; o.Y = a.o; o.ldy = st.H;
-    mega_gemv<false>(a, o, smem, s_part);
+    // P3: o_proj + residual: h1 = bf16(x + attn_out), partial sum of squares of the un-rounded sum
+    MEGA_FILL_BEGIN(sh)
+      q.W = wp->wo; q.N = st.H; q.K = st.heads * 128; q.T = T; q.xmode = X_PLAIN; q.X = a.attn; q.ldx = st.heads * 128;
+      q.epi = EPI_O_H1; q.R = a.x; q.ldr = st.H; q.Y = a.h1; q.ldy = st.H; q.ss_out = a.ssA;
+      q.next_W = wp->gate; q.next_W2 = wp->up; q.next_N = st.I; q.next_K = st.H;
+    MEGA_FILL_END()
+    mega_gemv<false>(a, sh.gp, smem);
     grid_sync(gb);
-    GemvP gu{};
-    gu.W = w.gate; gu.W2 = w.up; gu.N = st.I; gu.K = st.H; gu.T = T; gu.xmode = X_RESNORM; gu.X = a.o; gu.X2 = a.x; gu.ldx = st.H;
-    gu.norm_w = w.post_ln; gu.h1_out = a.h1; gu.epi = EPI_SWIGLU; gu.Y = a.act; gu.ldy = st.I;
-    mega_gemv<true>(a, gu, smem, s_part);
+    // P4: post-attention RMSNorm (scale from P3's partials, applied to the rounded h1) -> SwiGLU(gate, up)
+    MEGA_FILL_BEGIN(sh)
+      q.W = wp->gate; q.W2 = wp->up; q.N = st.I; q.K = st.H; q.T = T; q.xmode = X_NORM; q.X = a.h1; q.ldx = st.H;
+      q.norm_w = wp->post_ln; q.ss_in = a.ssA; q.epi = EPI_SWIGLU; q.Y = a.act; q.ldy = st.I;
+      q.next_W = wp->down; q.next_N = st.H; q.next_K = st.I;
+    MEGA_FILL_END()
+    mega_gemv<true>(a, sh.gp, smem);
     grid_sync(gb);
-    GemvP dn{};
-    dn.W = w.down; dn.N = st.H; dn.K = st.I; dn.T = T; dn.xmode = X_PLAIN; dn.X = a.act; dn.ldx = st.I;
-    dn.epi = EPI_RESIDUAL; dn.R = a.h1; dn.ldr = st.H; dn.Y = a.x; dn.ldy = st.H;
-    mega_gemv<false>(a, dn, smem, s_part);
+    // P5: down_proj + residual -> x
+    MEGA_FILL_BEGIN(sh)
+      q.W = wp->down; q.N = st.H; q.K = st.I; q.T = T; q.xmode = X_PLAIN; q.X = a.act; q.ldx = st.I;
+      q.epi = EPI_RESIDUAL; q.R = a.h1; q.ldr = st.H; q.Y = a.x; q.ldy = st.H; q.ss_out = a.ssB;
+      if (l + 1 < st.n_layers) {
+        q.next_W = st.layers[l + 1].wqkv; q.next_N = nh * 128; q.next_K = st.H;
+      } else {
+        q.next_W = after_W; q.next_N = after_N; q.next_K = after_K;
+      }
+    MEGA_FILL_END()
+    mega_gemv<false>(a, sh.gp, smem);
     grid_sync(gb);
   }
 }
@@ -494,50 +645,80 @@ __device__ __noinline__ void mega_finish(const MegaArgs& a, uint32_t* s_codes) {
     frame_finish_row(a.fs, tab, a.codec_emb, a.step_input, a.H, a.B, a.n_ac, b, s_codes);
 }
 
-__global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(const MegaArgs a) {
+__global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(const MegaArgs args) {
   extern __shared__ __align__(128) unsigned char mega_smem[];
-  __shared__ float s_part[128];
-  __shared__ uint32_t s_codes[16];
-  GridBar gb{a.bar, 0u};
+  __shared__ MegaShared sh;
+  {
+    // kernel parameters -> shared memory (taking their address would otherwise copy them to every thread's stack)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&args);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.a);
+    for (int i = threadIdx.x; i < (int)(sizeof(MegaArgs) / 4); i += MEGA_THREADS) dst[i] = src[i];
+    if (threadIdx.x == 0) s_prof_idx = g_prof_idx;
+  }
+  __syncthreads();
+  const MegaArgs& a = sh.a;
+  GridBar gb{a.bar, 0u, a.bar_mode};
   const int B = a.B;
+  if (a.bench_barriers > 0) {
+    for (int i = 0; i < a.bench_barriers; ++i) grid_sync(gb);
+    return;
+  }
   for (int frame = 0; frame < a.n_frames; ++frame) {
     if (a.do_cp) {
       // ---- code predictor: 15 dependent passes (code_predictor.rs:320-416) ----
-      if (blockIdx.x == 0 && threadIdx.x < a.n_ac * B) {
+      if (blockIdx.x == 0)
         for (int i = threadIdx.x; i < a.n_ac * B; i += MEGA_THREADS) a.fs.amax[i] = 0ull;
-      }
+      const int nh_cp = (a.cp.heads + 2 * a.cp.kv_heads) * 128;
       for (int g = 0; g < a.n_ac; ++g) {
         const int T = g == 0 ? 2 * B : B, S = g == 0 ? 2 : 1;
-        GemvP pr{};
-        pr.N = a.C; pr.K = a.H; pr.T = T; pr.xmode = g == 0 ? X_CP0 : X_CPG; pr.g = g;
-        pr.emb = g == 0 ? a.codec_emb : a.cp_emb[g - 1];
+        MEGA_FILL_BEGIN(sh)
+          q.N = a.C; q.K = a.H; q.T = T; q.xmode = g == 0 ? X_CP0 : X_CPG; q.g = g;
+          q.emb = g == 0 ? a.codec_emb : a.cp_emb[g - 1];
+          q.W = a.cp_proj_w; q.bias = a.cp_proj_b; q.epi = EPI_BIAS; q.Y = a.x; q.ldy = a.C; q.ss_out = a.ssB;
+          q.next_W = a.cp.layers[0].wqkv; q.next_N = nh_cp; q.next_K = a.C;
+        MEGA_FILL_END()
         if (a.cp_proj_w) {
-          pr.W = a.cp_proj_w; pr.bias = a.cp_proj_b; pr.epi = EPI_BIAS; pr.Y = a.x; pr.ldy = a.C;
-          mega_gemv<false>(a, pr, mega_smem, s_part);
-        } else {
+          mega_gemv<false>(a, sh.gp, mega_smem);
+        } else if (blockIdx.x == 0) {
           // no projection (talker hidden == CP hidden): the gathered rows are the layer input
-          bf16* xs = reinterpret_cast<bf16*>(mega_smem);
-          mega_stage_x(a, pr, xs, s_part);
-          if (blockIdx.x == 0)
-            for (int i = threadIdx.x; i < T * (a.H >> 3); i += MEGA_THREADS) {
-              int t = i / (a.H >> 3), q = i - t * (a.H >> 3);
-              *reinterpret_cast<uint4*>(a.x + (size_t)t * a.C + q * 8) = *reinterpret_cast<const uint4*>(xs + (size_t)t * (a.H + 32) + q * 8);
+          const int K8 = a.H >> 3;
+          for (int i = threadIdx.x; i < T * K8; i += MEGA_THREADS) {
+            const int t = i / K8, qq = i - t * K8;
+            const bf16* src;
+            if (g == 0) {
+              const int b = t >> 1;
+              src = (t & 1) ? a.codec_emb + (size_t)__ldcg(a.fs.cur_tok + b) * a.H : a.fs.last_hidden + (size_t)b * a.H;
+            } else {
+              src = a.cp_emb[g - 1] + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + t)) * a.H;
             }
+            *reinterpret_cast<uint4*>(a.x + (size_t)t * a.C + qq * 8) = ldcg16(src + qq * 8);
+          }
+          if (g == 0) { if (threadIdx.x < B) a.fs.frame_codes[threadIdx.x * 16] = __ldcg(a.fs.cur_tok + threadIdx.x); }
+          else if (threadIdx.x < B)
+            a.fs.frame_codes[threadIdx.x * 16 + g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + threadIdx.x));
         }
         grid_sync(gb);
-        mega_layers(a, a.cp, T, S, nullptr, g == 0 ? 0 : g + 1, a.cp_k, a.cp_v, a.cp_max_seq, a.cp_cos, a.cp_sin, mega_smem, s_part, gb);
-        GemvP hd{};
-        hd.W = a.cp_head[g]; hd.N = a.cpV; hd.K = a.C; hd.T = B; hd.xmode = X_RMSNORM; hd.norm_w = a.cp_norm;
-        hd.X = g == 0 ? a.x + a.C : a.x; hd.ldx = g == 0 ? 2 * a.C : a.C;
-        hd.epi = EPI_LOGITS; hd.amax = a.fs.amax + (size_t)g * B;
-        hd.Yf = a.cp_logits ? a.cp_logits + (size_t)g * B * a.cpV : nullptr;
-        mega_gemv<false>(a, hd, mega_smem, s_part);
+        mega_layers(sh, a.cp, T, S, nullptr, g == 0 ? 0 : g + 1, a.cp_k, a.cp_v, a.cp_max_seq, a.cp_cos, a.cp_sin, mega_smem,
+                    a.cp_proj_w ? a.ssB : nullptr, a.cp_head[g], a.cpV, a.C, gb);
+        MEGA_FILL_BEGIN(sh)
+          q.W = a.cp_head[g]; q.N = a.cpV; q.K = a.C; q.T = B; q.xmode = X_NORM; q.norm_w = a.cp_norm; q.ss_in = g == 0 ? nullptr : a.ssB;
+          q.X = g == 0 ? a.x + a.C : a.x; q.ldx = g == 0 ? 2 * a.C : a.C;
+          q.epi = EPI_LOGITS; q.amax = a.fs.amax + (size_t)g * B;
+          q.Yf = a.cp_logits ? a.cp_logits + (size_t)g * B * a.cpV : nullptr;
+          if (g + 1 < a.n_ac) {
+            if (a.cp_proj_w) { q.next_W = a.cp_proj_w; q.next_N = a.C; q.next_K = a.H; }
+            else { q.next_W = a.cp.layers[0].wqkv; q.next_N = nh_cp; q.next_K = a.C; }
+          } else if (a.do_talker) {
+            q.next_W = a.tk.layers[0].wqkv; q.next_N = (a.tk.heads + 2 * a.tk.kv_heads) * 128; q.next_K = a.H;
+          }
+        MEGA_FILL_END()
+        mega_gemv<false>(a, sh.gp, mega_smem);
         grid_sync(gb);
       }
     }
     if (a.do_finish) {
       // ---- emit the frame, build the talker input (lib.rs:605-622) ----
-      mega_finish(a, s_codes);
+      mega_finish(a, sh.codes);
       grid_sync(gb);
     }
     if (a.do_talker) {
@@ -546,11 +727,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
       for (int i = blockIdx.x * MEGA_THREADS + threadIdx.x; i < B * (a.H >> 3); i += gridDim.x * MEGA_THREADS)
         reinterpret_cast<uint4*>(a.x)[i] = ldcg16(reinterpret_cast<const uint4*>(in) + i);
       grid_sync(gb);
-      mega_layers(a, a.tk, B, 1, a.fs.offset, 0, a.tk_k, a.tk_v, a.max_seq, a.t_cos, a.t_sin, mega_smem, s_part, gb);
-      GemvP hd{};
-      hd.W = a.codec_head; hd.N = a.V; hd.K = a.H; hd.T = B; hd.xmode = X_RMSNORM; hd.norm_w = a.t_norm; hd.X = a.x; hd.ldx = a.H;
-      hd.xn_out = a.fs.last_hidden; hd.epi = EPI_LOGITS; hd.Yf = a.logits;
-      mega_gemv<false>(a, hd, mega_smem, s_part);
+      mega_layers(sh, a.tk, B, 1, a.fs.offset, 0, a.tk_k, a.tk_v, a.max_seq, a.t_cos, a.t_sin, mega_smem, nullptr,
+                  a.codec_head, a.V, a.H, gb);
+      MEGA_FILL_BEGIN(sh)
+        q.W = a.codec_head; q.N = a.V; q.K = a.H; q.T = B; q.xmode = X_NORM; q.norm_w = a.t_norm; q.X = a.x; q.ldx = a.H;
+        q.ss_in = a.ssB;
+        q.xn_out = a.fs.last_hidden; q.epi = EPI_LOGITS; q.Yf = a.logits;
+        if (a.do_cp && frame + 1 < a.n_frames) {       // the next frame starts with the CP projection (or its first layer)
+          if (a.cp_proj_w) { q.next_W = a.cp_proj_w; q.next_N = a.C; q.next_K = a.H; }
+          else { q.next_W = a.cp.layers[0].wqkv; q.next_N = (a.cp.heads + 2 * a.cp.kv_heads) * 128; q.next_K = a.C; }
+        }
+      MEGA_FILL_END()
+      mega_gemv<false>(a, sh.gp, mega_smem);
       grid_sync(gb);
     }
     if (a.do_sample) {
@@ -566,20 +754,23 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
   }
 }
 
-static size_t mega_smem_bytes(const q3_model_desc& d, int B, int max_seq) {
-  auto gemv = [](int T, int K, bool dual) {
-    const int T8 = (T + 7) & ~7;
-    size_t xs = (((size_t)T8 * (K + 32) * 2) + 127) & ~(size_t)127;
-    return xs + (size_t)16 * (T8 / 8) * (dual ? 2 : 1) * 16 * 8 * 4;
+// Shared memory of the persistent kernel for a given model / batch / grid; returns 0 when a phase does not fit
+// the kernel's static limits (then the multi-kernel path is used).
+static size_t mega_smem_bytes(const q3_model_desc& d, int B, int max_seq, int grid) {
+  size_t red_max = 0;
+  bool ok = true;
+  auto phase = [&](int N, int T, bool dual) {
+    const int units = N / 8, per_cta = (units + grid - 1) / grid, tiles = (per_cta + 1) / 2;
+    if (tiles > MEGA_MAX_TILES || T > MEGA_TMAX || N % 8 != 0) ok = false;
+    const int NT = (T + 7) / 8;
+    red_max = std::max(red_max, (size_t)tiles * 16 * NT * (dual ? 2 : 1) * 16 * 8 * 4);
   };
+  const int nh = (d.heads + 2 * d.kv_heads) * 128, cnh = (d.cp_heads + 2 * d.cp_kv_heads) * 128;
+  phase(nh, B, false); phase(d.hidden, B, false); phase(d.inter, B, true); phase(d.codec_vocab, B, false);
+  phase(d.cp_hidden, 2 * B, false); phase(cnh, 2 * B, false); phase(d.cp_inter, 2 * B, true); phase(d.cp_vocab, B, false);
+  if (!ok) return 0;
   size_t m = sizeof(SampleSmem);
-  m = std::max(m, gemv(B, d.hidden, true));
-  m = std::max(m, gemv(B, d.inter, false));
-  m = std::max(m, gemv(B, d.heads * 128, false));
-  m = std::max(m, gemv(2 * B, d.hidden, false));
-  m = std::max(m, gemv(2 * B, d.cp_hidden, true));
-  m = std::max(m, gemv(2 * B, d.cp_inter, false));
-  m = std::max(m, gemv(2 * B, d.cp_heads * 128, false));
+  m = std::max(m, (size_t)(MEGA_TMAX + MEGA_MAX_TILES * 16 * MEGA_TMAX) * 4 + red_max);
   m = std::max(m, (size_t)(2 * std::max(max_seq, d.cp_max_seq) + 256 + 16 * 2 * 128) * 4);
   return m;
 }

@@ -43,9 +43,10 @@ struct q3_session {
   bool prefilled = false, first_sampled = false;
   // persistent frame kernel (batch <= 8)
   bool use_mega = false;
+  DBuf prof;                       // optional timestamp buffer (q3_debug_profile)
   size_t mega_smem = 0;
   int mega_grid = 0;
-  DBuf bar;
+  DBuf bar, ss;
   // frame graph
   cudaGraphExec_t graph_exec = nullptr;
   bool graph_ok = false;
@@ -312,16 +313,25 @@ static MegaArgs mega_args(q3_session* s) {
   a.h1 = s->sc.h1.as<bf16>(); a.act = s->sc.act.as<bf16>(); a.step_input = s->step_input.as<bf16>();
   a.logits = s->logits.as<float>();
   a.bar = s->bar.as<unsigned>();
+  a.ssA = s->ss.as<float>();
+  a.ssB = s->ss.as<float>() + (size_t)s->mega_grid * MEGA_TMAX;
   SampleArgs sa = make_sample_args(s->cfg, d.codec_vocab, s->B);
   sa.logits = s->logits.as<float>();
   sa.seen = s->fs.seen; sa.rng = s->fs.rng; sa.tok_out = s->fs.cur_tok; sa.token_count = s->fs.token_count;
   sa.done = s->fs.done; sa.offset = s->fs.offset; sa.frame_idx = s->fs.frame_idx; sa.host_flags = nullptr; sa.advance = 1;
   a.smp = sa;
+  const char* e1 = std::getenv("Q3_BAR_MODE");
+  const char* e2 = std::getenv("Q3_PREFETCH");
+  a.bar_mode = e1 ? std::atoi(e1) : 0;
+  a.prefetch_mode = e2 ? std::atoi(e2) : 2;
+  const char* e3 = std::getenv("Q3_DBG");
+  a.dbg = e3 ? std::atoi(e3) : 0;
   return a;
 }
 
 static void mega_launch(q3_session* s, MegaArgs& a) {
   Q3_CHECK_CUDA(cudaMemsetAsync(s->bar.p, 0, 4, s->st));
+  if (s->prof.p) { a.prof = s->prof.as<unsigned long long>(); a.prof_cap = (int)(s->prof.bytes / 8); }
   void* params[] = {(void*)&a};
   Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega_kernel, dim3(s->mega_grid), dim3(MEGA_THREADS), params,
                                             s->mega_smem, s->st));
@@ -705,10 +715,10 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
     // persistent frame kernel: batch <= 8 (16 tokens in the CP prefill pass), needs one resident CTA per SM
     const char* env = std::getenv("Q3_MEGA");
     const bool want = !(env && env[0] == '0');
-    s->mega_smem = mega_smem_bytes(d, B, max_seq);
+    s->mega_smem = mega_smem_bytes(d, B, max_seq, m->num_sms);
     s->bar.alloc(64);
     s->bar.zero();
-    if (want && 2 * B <= MEGA_TMAX && s->mega_smem <= 227 * 1024 && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 &&
+    if (want && 2 * B <= MEGA_TMAX && s->mega_smem > 0 && s->mega_smem <= 227 * 1024 && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 &&
         d.inter % 32 == 0 && d.cp_inter % 32 == 0 && d.codec_vocab % 16 == 0 && d.cp_vocab % 16 == 0) {
       Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->mega_smem));
       int per_sm = 0;
@@ -716,6 +726,8 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
       if (per_sm >= 1) {
         s->use_mega = true;
         s->mega_grid = m->num_sms;
+        s->ss.alloc((size_t)2 * s->mega_grid * MEGA_TMAX * 4);
+        s->ss.zero();
       }
     }
   }
@@ -1152,6 +1164,43 @@ q3_status q3_fused_residual_rmsnorm_host(const void* x, const void* r, const voi
   Q3_CHECK_CUDA(cudaDeviceSynchronize());
   Q3_CHECK_CUDA(cudaMemcpy(out_normed, dn.p, n, cudaMemcpyDeviceToHost));
   Q3_CHECK_CUDA(cudaMemcpy(out_sum, dsum.p, n, cudaMemcpyDeviceToHost));
+  Q3_API_END
+}
+
+// Debug aid (not part of the drop-in boundary): run `frames` frames with %globaltimer stamps of block 0 and return
+// them as (time_ns << 8 | tag).  Used by tools/profile_mega.py only.
+q3_status q3_debug_profile(q3_session* s, int32_t frames, uint64_t* stamps, int32_t cap, int32_t* n_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && stamps && n_out && s->use_mega && s->prefilled, Q3_ERR_STATE, "profile needs a prefilled session on the persistent path");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  sample_first_if_needed(s);
+  s->prof.alloc((size_t)cap * 8);
+  s->prof.zero(s->st);
+  unsigned zero = 0;
+  Q3_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_prof_idx, &zero, 4, 0, cudaMemcpyHostToDevice, s->st));
+  run_frames(s, frames);
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  unsigned n = 0;
+  Q3_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_prof_idx, 4));
+  *n_out = (int)std::min<unsigned>(n, (unsigned)cap);
+  Q3_CHECK_CUDA(cudaMemcpy(stamps, s->prof.p, (size_t)(*n_out) * 8, cudaMemcpyDeviceToHost));
+  s->prof.release();
+  Q3_API_END
+}
+
+// Debug aid: time `n` back-to-back grid barriers of the persistent kernel (ms for the whole launch).
+q3_status q3_debug_barrier_bench(q3_session* s, int32_t n, float* ms_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && ms_out && s->use_mega, Q3_ERR_STATE, "needs the persistent path");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  MegaArgs a = mega_args(s);
+  a.bench_barriers = n;
+  mega_launch(s, a);
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
+  mega_launch(s, a);
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  Q3_CHECK_CUDA(cudaEventElapsedTime(ms_out, s->ev0, s->ev1));
   Q3_API_END
 }
 
