@@ -46,7 +46,13 @@ struct LayerW {
 struct StackDims { int H, I, heads, kv_heads, layers; };
 
 // ---- vocoder ----------------------------------------------------------------------------------------
-struct VConv { const float* w = nullptr; const float* b = nullptr; int cin = 0, cout = 0, k = 1; };
+struct VConv {
+  const float* w = nullptr;       // SIMT layout [Cin*k][Cout]
+  const float* b = nullptr;
+  int cin = 0, cout = 0, k = 1;
+  const bf16 *w_hi = nullptr, *w_lo = nullptr;   // tensor-core layout: bf16 hi/lo split, [k][chunks][Cout_pad][32]
+  int cout_pad = 0, chunks = 0;
+};
 struct VSnake { const float* ea = nullptr; const float* ib = nullptr; };
 struct VLayer { const float *in_ln, *post_ln, *attn_scale, *mlp_scale; VConv q, k, v, o, gate, up, down; };
 struct VConvNext { const float *dw_w, *dw_b, *ln_w, *ln_b, *gamma; VConv pw1, pw2; int C; };

@@ -3,8 +3,11 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "model.h"
 #include "vocoder_kernels.cuh"
+#include "vocoder_mma.cuh"
 
 namespace {
 
@@ -49,6 +52,21 @@ VConv make_conv(q3_model* m, const std::string& wname, const std::string& bname,
   c.w = packed.as<float>();
   m->owned.push_back(std::move(packed));
   if (!bname.empty()) c.b = needp(m, bname);
+  // tensor-core layout (bf16 hi/lo split)
+  c.cout_pad = ceil_div(c.cout, MC_BM) * MC_BM;
+  c.chunks = ceil_div(c.cin, MC_BK);
+  const size_t np = (size_t)c.k * c.chunks * c.cout_pad * MC_BK;
+  DBuf hi, lo;
+  hi.alloc(np * sizeof(bf16));
+  lo.alloc(np * sizeof(bf16));
+  voc_pack_mma_weights_kernel<<<512, 256>>>(w.buf.as<float>(), hi.as<bf16>(), lo.as<bf16>(), c.cout, c.cin, c.k, c.cout_pad, c.chunks,
+                                            transposed ? 1 : 0);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  c.w_hi = hi.as<bf16>();
+  c.w_lo = lo.as<bf16>();
+  m->owned.push_back(std::move(hi));
+  m->owned.push_back(std::move(lo));
   return c;
 }
 
@@ -68,8 +86,43 @@ VSnake make_snake(q3_model* m, const std::string& prefix) {
   return s;
 }
 
+bool use_mma_path() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("Q3_VOC_SIMT");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+void launch_mma(MmaConvArgs& a, int grid_q, int Cout_pad, int z, cudaStream_t st) {
+  static bool configured = false;
+  const size_t smem = mma_conv_smem_bytes(a.max_shift - a.min_shift);
+  if (!configured) {
+    Q3_CHECK_CUDA(cudaFuncSetAttribute(voc_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  Q3_REQUIRE(smem <= 100 * 1024, Q3_ERR_UNSUPPORTED, "conv window too large for the staged tile");
+  voc_conv_mma_kernel<<<dim3(grid_q, Cout_pad / MC_BM, z), 256, smem, st>>>(a);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+
 void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil, const VSnake* snake, const float* res,
                  const float* scale, int epi, cudaStream_t st) {
+  if (use_mma_path() && c.cout >= 16 && c.k <= MC_MAX_TAPS) {
+    MmaConvArgs m{};
+    m.x = x; m.w_hi = c.w_hi; m.w_lo = c.w_lo; m.bias = c.b;
+    m.snake_a = snake ? snake->ea : nullptr; m.snake_ib = snake ? snake->ib : nullptr;
+    m.res = res; m.scale = scale; m.y = y;
+    m.B = B; m.Cin = c.cin; m.Cout = c.cout; m.Cout_pad = c.cout_pad; m.Tin = T; m.Tout = T; m.Q = T;
+    m.ntaps = c.k;
+    for (int j = 0; j < c.k; ++j) { m.tap_w[j] = j; m.tap_shift[j] = -(c.k - 1 - j) * dil; }
+    m.min_shift = -(c.k - 1) * dil; m.max_shift = 0;
+    m.out_stride = 1; m.out_off = 0; m.epi = epi; m.phases = 1; m.phase_tap_step = 0;
+    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B, st);
+    return;
+  }
   ConvArgs a;
   a.x = x; a.w = c.w; a.bias = c.b;
   a.snake_a = snake ? snake->ea : nullptr; a.snake_ib = snake ? snake->ib : nullptr;
@@ -85,6 +138,26 @@ void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil
 
 void launch_tconv(const VConv& c, int stride, const float* x, float* y, int B, int T, const VSnake* snake, cudaStream_t st) {
   Q3_REQUIRE(c.k <= 2 * stride && c.k >= stride, Q3_ERR_UNSUPPORTED, "transposed conv needs stride <= k <= 2*stride");
+  if (use_mma_path() && c.cout >= 16 && (c.k == stride || c.k == 2 * stride)) {
+    // phase r in [0, stride): y[co][stride*q + r] = b + sum_ci x[ci][q] w[ci][co][r] (+ x[ci][q-1] w[ci][co][r+stride])
+    MmaConvArgs m{};
+    m.x = x; m.w_hi = c.w_hi; m.w_lo = c.w_lo; m.bias = c.b;
+    m.snake_a = snake ? snake->ea : nullptr; m.snake_ib = snake ? snake->ib : nullptr;
+    m.y = y; m.B = B; m.Cin = c.cin; m.Cout = c.cout; m.Cout_pad = c.cout_pad; m.Tin = T; m.Tout = T * stride; m.Q = T;
+    if (c.k == 2 * stride) {
+      m.ntaps = 2;
+      m.tap_w[0] = stride; m.tap_shift[0] = -1;
+      m.tap_w[1] = 0; m.tap_shift[1] = 0;
+      m.min_shift = -1;
+    } else {
+      m.ntaps = 1;
+      m.tap_w[0] = 0; m.tap_shift[0] = 0;
+      m.min_shift = 0;
+    }
+    m.max_shift = 0; m.out_stride = stride; m.out_off = 0; m.epi = CEPI_NONE; m.phases = stride; m.phase_tap_step = 1;
+    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B * stride, st);
+    return;
+  }
   TConvArgs a;
   a.x = x; a.w = c.w; a.bias = c.b;
   a.snake_a = snake ? snake->ea : nullptr; a.snake_ib = snake ? snake->ib : nullptr;
