@@ -182,10 +182,11 @@ def main():
     tts = api.Qwen3TTS.from_weights(spec, tw, vw, device=local_rank)
     lib = L.load()
 
+    from qwen3_tts_rs_b200 import shard
     B, F = args.batch, args.frames
-    first = rank * B
+    first, last = shard.shard_range(B * world, rank, world)       # weak scaling: B utterances per GPU
     prompts = build_prompts(spec, B, first)
-    seeds = [42 + first + i for i in range(B)]
+    seeds = shard.utterance_seeds(42, first, last)
     opts = api.SynthesisOptions(max_length=F)
     pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
     lmax = max(len(p[0]) for p in pp)
@@ -252,6 +253,7 @@ def main():
     e1.record(stream)
     sess.synchronize()
     loop_ms = e0.elapsed_time(e1)
+    prefill_ms = sess.timing().prefill_ms
     _, nfr = sess.get_codes(F)
     frames_run = int(max(nfr)) if len(nfr) else F
 
@@ -263,6 +265,9 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     frames_step = int(n.sum())
+    # the only collective of the path: per-utterance frame counts gathered to every rank
+    all_counts = shard.gather_frame_counts(n.tolist(), B * world, rank, world, device="cuda")
+    assert int(all_counts.sum()) >= frames_step
 
     times = torch.tensor([ms_dev, e2e_s * 1e3, loop_ms], dtype=torch.float64, device="cuda")
     fr = torch.tensor([float(frames_step)], dtype=torch.float64, device="cuda")
@@ -294,8 +299,10 @@ def main():
                        "vocoder_dtype": "f32"},
             "breakdown_ms_per_step": {"decode_loop": loop_ms_max, "frames_in_loop": frames_run,
                                       "ms_per_frame": loop_ms_max / max(1, frames_run),
-                                      "vocoder": dec_ms / args.steps},
-            "roofline": {"kernel": "decode frame (one CUDA-graph replay: code-predictor frame + talker step + sampler, all rows)",
+                                      "vocoder": dec_ms / args.steps, "prefill": prefill_ms,
+                                      "vocoder_tflops_f32_equiv": (total_frames_step / world) * 4.959e9 / (dec_ms / args.steps / 1e3) / 1e12},
+            "roofline": {"kernel": "decode_frames_mega_kernel, per frame (one persistent cooperative launch runs 16 frames: 15 code-predictor "
+                                   "passes + 28-layer talker step + codec head + sampler for all rows)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "peak_source": peak_src, "traffic": None,
                          "algorithmic_bytes_per_launch": bytes_step, "launch_ms": t_frame * 1e3},
