@@ -8,6 +8,7 @@
 #include <cstdlib>
 
 #include "decode_kernels.cuh"
+#include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "mega.cuh"
 #include "model.h"
@@ -18,9 +19,18 @@ static thread_local std::string g_last_error;
 // =================================================================================================
 // session object
 struct Scratch {
-  DBuf x, qkv, q, attn, o, normed, h1, act, tmp_e, tmp_p;
+  DBuf x, qkv, q, attn, o, normed, h1, act, tmp_e, tmp_p, zeros;
   int tcap = 0;
 };
+
+static bool use_tc_gemm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("Q3_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 
 struct q3_session {
   const q3_model* m = nullptr;
@@ -118,6 +128,8 @@ static void ensure_scratch(q3_session* s, int T) {
   sc.act.alloc((size_t)T * I * 2);
   sc.tmp_e.alloc((size_t)T * E * 2);
   sc.tmp_p.alloc((size_t)T * E * 2);
+  sc.zeros.alloc((size_t)T * H * 2);
+  sc.zeros.zero(s->st);
   sc.tcap = T;
 }
 
@@ -131,12 +143,25 @@ static void layers_forward(q3_session* s, const std::vector<LayerW>& L, const St
   const int nh = dm.heads + 2 * dm.kv_heads;
   const float eps = m->d.rms_eps;
   const size_t layer_stride = (size_t)s->B * dm.kv_heads * cache_seq * 128;
+  // multi-position passes (prompt prefill, S > 1) run their projections on the tcgen05 + TMA GEMM -- for every batch
+  // size, so that a row's result never depends on how many other rows share the launch
+  const bool tc = use_tc_gemm() && S > 1 && gemm_tc_supported(nh * 128, dm.H, T, dm.H, EPI_STORE) &&
+                  gemm_tc_supported(dm.H, dm.heads * 128, T, dm.heads * 128, EPI_STORE) &&
+                  gemm_tc_supported(dm.I, dm.H, T, dm.H, EPI_SWIGLU) && gemm_tc_supported(dm.H, dm.I, T, dm.I, EPI_RESIDUAL);
   for (int l = 0; l < dm.layers; ++l) {
     const LayerW& w = L[l];
-    GemvArgs g{};
-    g.W = w.wqkv; g.X = x; g.ldx = dm.H; g.norm_w = w.in_ln; g.eps = eps; g.N = nh * 128; g.K = dm.H; g.T = T;
-    g.pro = PRO_RMSNORM; g.epi = EPI_STORE; g.Y = sc.qkv.as<bf16>(); g.ldy = nh * 128;
-    gemv_launch(g, m->num_sms, s->st);
+    if (tc) {
+      // input RMSNorm (rms_norm(x) == fused kernel with a zero residual), then [q;k;v] = xn W^T
+      fused_residual_rmsnorm_launch<bf16>(x, sc.zeros.as<bf16>(), w.in_ln, sc.normed.as<bf16>(), sc.h1.as<bf16>(), T, dm.H, eps, s->st);
+      GemmTcArgs ga{};
+      ga.N = nh * 128; ga.K = dm.H; ga.T = T; ga.epi = EPI_STORE; ga.Y = sc.qkv.as<bf16>(); ga.ldy = nh * 128;
+      gemm_tc_launch(w.wqkv, nullptr, sc.normed.as<bf16>(), dm.H, ga, s->st);
+    } else {
+      GemvArgs g{};
+      g.W = w.wqkv; g.X = x; g.ldx = dm.H; g.norm_w = w.in_ln; g.eps = eps; g.N = nh * 128; g.K = dm.H; g.T = T;
+      g.pro = PRO_RMSNORM; g.epi = EPI_STORE; g.Y = sc.qkv.as<bf16>(); g.ldy = nh * 128;
+      gemv_launch(g, m->num_sms, s->st);
+    }
 
     RopeArgs r{};
     r.qkv = sc.qkv.as<bf16>(); r.q_out = sc.q.as<bf16>();
@@ -156,23 +181,38 @@ static void layers_forward(q3_session* s, const std::vector<LayerW>& L, const St
     Q3_COUNT_LAUNCH();
     Q3_LAUNCH_CHECK();
 
-    GemvArgs o{};
-    o.W = w.wo; o.X = sc.attn.as<bf16>(); o.ldx = dm.heads * 128; o.N = dm.H; o.K = dm.heads * 128; o.T = T;
-    o.pro = PRO_NONE; o.epi = EPI_STORE; o.Y = sc.o.as<bf16>(); o.ldy = dm.H;
-    gemv_launch(o, m->num_sms, s->st);
+    if (tc) {
+      GemmTcArgs ga{};
+      ga.N = dm.H; ga.K = dm.heads * 128; ga.T = T; ga.epi = EPI_STORE; ga.Y = sc.o.as<bf16>(); ga.ldy = dm.H;
+      gemm_tc_launch(w.wo, nullptr, sc.attn.as<bf16>(), dm.heads * 128, ga, s->st);
+    } else {
+      GemvArgs o{};
+      o.W = w.wo; o.X = sc.attn.as<bf16>(); o.ldx = dm.heads * 128; o.N = dm.H; o.K = dm.heads * 128; o.T = T;
+      o.pro = PRO_NONE; o.epi = EPI_STORE; o.Y = sc.o.as<bf16>(); o.ldy = dm.H;
+      gemv_launch(o, m->num_sms, s->st);
+    }
 
     fused_residual_rmsnorm_launch<bf16>(sc.o.as<bf16>(), x, w.post_ln, sc.normed.as<bf16>(), sc.h1.as<bf16>(), T, dm.H,
                                         eps, s->st);
 
-    GemvArgs gu{};
-    gu.W = w.gate; gu.W2 = w.up; gu.X = sc.normed.as<bf16>(); gu.ldx = dm.H; gu.N = dm.I; gu.K = dm.H; gu.T = T;
-    gu.pro = PRO_NONE; gu.epi = EPI_SWIGLU; gu.Y = sc.act.as<bf16>(); gu.ldy = dm.I;
-    gemv_launch(gu, m->num_sms, s->st);
+    if (tc) {
+      GemmTcArgs gu{};
+      gu.N = dm.I; gu.K = dm.H; gu.T = T; gu.epi = EPI_SWIGLU; gu.Y = sc.act.as<bf16>(); gu.ldy = dm.I;
+      gemm_tc_launch(w.gate, w.up, sc.normed.as<bf16>(), dm.H, gu, s->st);
+      GemmTcArgs dn{};
+      dn.N = dm.H; dn.K = dm.I; dn.T = T; dn.epi = EPI_RESIDUAL; dn.R = sc.h1.as<bf16>(); dn.ldr = dm.H; dn.Y = x; dn.ldy = dm.H;
+      gemm_tc_launch(w.down, nullptr, sc.act.as<bf16>(), dm.I, dn, s->st);
+    } else {
+      GemvArgs gu{};
+      gu.W = w.gate; gu.W2 = w.up; gu.X = sc.normed.as<bf16>(); gu.ldx = dm.H; gu.N = dm.I; gu.K = dm.H; gu.T = T;
+      gu.pro = PRO_NONE; gu.epi = EPI_SWIGLU; gu.Y = sc.act.as<bf16>(); gu.ldy = dm.I;
+      gemv_launch(gu, m->num_sms, s->st);
 
-    GemvArgs dn{};
-    dn.W = w.down; dn.X = sc.act.as<bf16>(); dn.ldx = dm.I; dn.N = dm.H; dn.K = dm.I; dn.T = T;
-    dn.pro = PRO_NONE; dn.epi = EPI_RESIDUAL; dn.R = sc.h1.as<bf16>(); dn.ldr = dm.H; dn.Y = x; dn.ldy = dm.H;
-    gemv_launch(dn, m->num_sms, s->st);
+      GemvArgs dn{};
+      dn.W = w.down; dn.X = sc.act.as<bf16>(); dn.ldx = dm.I; dn.N = dm.H; dn.K = dm.I; dn.T = T;
+      dn.pro = PRO_NONE; dn.epi = EPI_RESIDUAL; dn.R = sc.h1.as<bf16>(); dn.ldr = dm.H; dn.Y = x; dn.ldy = dm.H;
+      gemv_launch(dn, m->num_sms, s->st);
+    }
   }
 }
 
@@ -184,13 +224,23 @@ static void text_project(q3_session* s, const int* ids_dev, int n, bf16* out) {
   gather_rows_kernel<<<n, 128, 0, s->st>>>(m->text_emb, ids_dev, d.text_embed_dim, d.text_vocab, s->sc.tmp_e.as<bf16>());
   Q3_COUNT_LAUNCH();
   Q3_LAUNCH_CHECK();
+  const int E = d.text_embed_dim;
+  if (use_tc_gemm() && gemm_tc_supported(E, E, n, E, EPI_BIAS_SILU) && gemm_tc_supported(d.hidden, E, n, E, EPI_BIAS)) {
+    GemmTcArgs a{};
+    a.N = E; a.K = E; a.T = n; a.epi = EPI_BIAS_SILU; a.bias = m->fc1_b; a.Y = s->sc.tmp_p.as<bf16>(); a.ldy = E;
+    gemm_tc_launch(m->fc1_w, nullptr, s->sc.tmp_e.as<bf16>(), E, a, s->st);
+    GemmTcArgs b{};
+    b.N = d.hidden; b.K = E; b.T = n; b.epi = EPI_BIAS; b.bias = m->fc2_b; b.Y = out; b.ldy = d.hidden;
+    gemm_tc_launch(m->fc2_w, nullptr, s->sc.tmp_p.as<bf16>(), E, b, s->st);
+    return;
+  }
   GemvArgs a{};
-  a.W = m->fc1_w; a.bias = m->fc1_b; a.X = s->sc.tmp_e.as<bf16>(); a.ldx = d.text_embed_dim; a.N = d.text_embed_dim;
-  a.K = d.text_embed_dim; a.T = n; a.pro = PRO_NONE; a.epi = EPI_BIAS_SILU; a.Y = s->sc.tmp_p.as<bf16>(); a.ldy = d.text_embed_dim;
+  a.W = m->fc1_w; a.bias = m->fc1_b; a.X = s->sc.tmp_e.as<bf16>(); a.ldx = E; a.N = E;
+  a.K = E; a.T = n; a.pro = PRO_NONE; a.epi = EPI_BIAS_SILU; a.Y = s->sc.tmp_p.as<bf16>(); a.ldy = E;
   gemv_launch(a, m->num_sms, s->st);
   GemvArgs b{};
-  b.W = m->fc2_w; b.bias = m->fc2_b; b.X = s->sc.tmp_p.as<bf16>(); b.ldx = d.text_embed_dim; b.N = d.hidden;
-  b.K = d.text_embed_dim; b.T = n; b.pro = PRO_NONE; b.epi = EPI_BIAS; b.Y = out; b.ldy = d.hidden;
+  b.W = m->fc2_w; b.bias = m->fc2_b; b.X = s->sc.tmp_p.as<bf16>(); b.ldx = E; b.N = d.hidden;
+  b.K = E; b.T = n; b.pro = PRO_NONE; b.epi = EPI_BIAS; b.Y = out; b.ldy = d.hidden;
   gemv_launch(b, m->num_sms, s->st);
 }
 

@@ -123,6 +123,16 @@ void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil
     launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B, st);
     return;
   }
+  if (c.cout == 1 && dil == 1 && res == nullptr && scale == nullptr && (epi == CEPI_NONE || epi == CEPI_CLAMP)) {
+    // SIMT layout [Cin*k][Cout] with Cout == 1 is exactly [Cin][k]
+    const size_t smem = (size_t)(32 * (256 + c.k - 1) + 32 * c.k) * sizeof(float);
+    voc_conv_cout1_kernel<<<dim3(ceil_div(T, 256), B), 256, smem, st>>>(x, c.w, c.b, snake ? snake->ea : nullptr,
+                                                                        snake ? snake->ib : nullptr, y, c.cin, T, c.k,
+                                                                        epi == CEPI_CLAMP ? 1 : 0);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    return;
+  }
   ConvArgs a;
   a.x = x; a.w = c.w; a.bias = c.b;
   a.snake_a = snake ? snake->ea : nullptr; a.snake_ib = snake ? snake->ib : nullptr;

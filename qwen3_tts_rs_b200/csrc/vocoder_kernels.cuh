@@ -56,9 +56,56 @@ struct ConvArgs {
 
 constexpr int CV_BM = 64, CV_BN = 64, CV_BK = 16;
 
+// sin with one explicit 2*pi range reduction (two FMAs, Cody-Waite split) followed by the SFU sine: absolute
+// error ~1e-6 for |x| up to a few thousand, at a fraction of sinf()'s instruction count.  The vocoder spends a
+// large share of its non-tensor time here (every conv operand goes through SnakeBeta).
+__device__ __forceinline__ float sin_reduced(float x) {
+  const float k = rintf(x * 0.15915494309189535f);          // x / (2*pi)
+  float r = fmaf(k, -6.28318548202514648f, x);              // 2*pi high part (f32)
+  r = fmaf(k, 1.74845553e-7f, r);                           // 2*pi low part: 2*pi = 6.28318548.. - 1.748e-7
+  return __sinf(r);
+}
 __device__ __forceinline__ float snake_f(float x, float a, float ib) {
-  float s = sinf(x * a);
+  float s = sin_reduced(x * a);
   return x + (s * s) * ib;
+}
+
+// Final conv of the vocoder: Cout == 1 (96 -> 1, k = 7), SnakeBeta prologue, clamp epilogue.  HBM-bound
+// (reads C*T floats once, writes T): each block stages snake(x) for 256 positions + halo, 32 channels at a
+// time, and every thread owns one output position.
+__global__ void __launch_bounds__(256) voc_conv_cout1_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cin*k]*/,
+                                                             const float* __restrict__ bias, const float* __restrict__ snake_a,
+                                                             const float* __restrict__ snake_ib, float* __restrict__ y, int Cin,
+                                                             int T, int k, int clamp) {
+  extern __shared__ float sm_c1[];
+  const int halo = k - 1, W = 256 + halo;
+  float* xs = sm_c1;                    // [32][W]
+  float* ws = sm_c1 + 32 * W;           // [32][k]
+  const int b = blockIdx.y, t0 = blockIdx.x * 256, tid = threadIdx.x;
+  const float* xb = x + (size_t)b * Cin * T;
+  float acc = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += 32) {
+    __syncthreads();
+    for (int i = tid; i < 32 * W; i += 256) {
+      const int ci = i / W, p = i - ci * W, t = t0 - halo + p;
+      float v = 0.f;
+      if (c0 + ci < Cin && t >= 0 && t < T) {
+        v = xb[(size_t)(c0 + ci) * T + t];
+        if (snake_a) v = snake_f(v, snake_a[c0 + ci], snake_ib[c0 + ci]);
+      }
+      xs[i] = v;
+    }
+    for (int i = tid; i < 32 * k; i += 256) ws[i] = (c0 + i / k < Cin) ? w[(size_t)c0 * k + i] : 0.f;
+    __syncthreads();
+    for (int ci = 0; ci < 32; ++ci)
+      for (int j = 0; j < k; ++j) acc = fmaf(ws[ci * k + j], xs[ci * W + tid + j], acc);
+  }
+  const int t = t0 + tid;
+  if (t < T) {
+    float v = acc + (bias ? bias[0] : 0.f);
+    if (clamp) v = fminf(fmaxf(v, -1.0f), 1.0f);
+    y[(size_t)b * T + t] = v;
+  }
 }
 
 // 256 threads; thread (ty = tid/16, tx = tid%16) computes rows ty*4..+3 (co) x cols tx, tx+16, tx+32, tx+48 (t).
