@@ -205,26 +205,6 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
   }
   if (a.prefetch_mode >= 1) mega_prefetch_rows(p.W, p.W2, p.N, K);
   prof_stamp(a, 1);
-  if (NORM) {
-    // row scales: one warp per token
-    for (int t = warp; t < T; t += MEGA_WARPS) {
-      float tot = 0.f;
-      if (p.ss_in != nullptr) {
-        for (int c = lane; c < (int)gridDim.x; c += 32) tot += __ldcg(p.ss_in + c * MEGA_TMAX + t);
-      } else {
-        const bf16* xr = p.X + (size_t)t * p.ldx;
-        for (int c = 8 * lane; c < K; c += 256) {
-          float f[8];
-          unpack8(ldcg16(xr + c), f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) tot = fmaf(f[e], f[e], tot);
-        }
-      }
-      tot = warp_sum_xor(tot);
-      if (lane == 0) scale_s[t] = ref_mean_rsqrt(tot, K, a.eps);
-    }
-    __syncthreads();
-  }
   prof_stamp(a, 2);
   // this lane's activation rows: token nt*8 + g of each n-tile
   const bf16* xrow[NT];
@@ -243,7 +223,6 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
       } else {
         xrow[nt] = p.X + (size_t)t * p.ldx;
       }
-      if (NORM) xsc[nt] = scale_s[t];
     }
   }
   if (blockIdx.x == 0) {
@@ -321,6 +300,38 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
   };
   float acc[NM][NT][4];
   load_chunk(0, 0);
+  if (NORM) {
+    // row scales, computed while the first chunk's loads are in flight: one warp per token
+    for (int t = warp; t < T; t += MEGA_WARPS) {
+      float tot = 0.f;
+      if (p.ss_in != nullptr) {
+        float part[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int c = lane + 32 * i;
+          part[i] = c < (int)gridDim.x ? __ldcg(p.ss_in + c * MEGA_TMAX + t) : 0.f;
+        }
+        tot = ((part[0] + part[1]) + (part[2] + part[3])) + part[4];
+        for (int c = lane + 160; c < (int)gridDim.x; c += 32) tot += __ldcg(p.ss_in + c * MEGA_TMAX + t);
+      } else {
+        const bf16* xr = p.X + (size_t)t * p.ldx;
+        for (int c = 8 * lane; c < K; c += 256) {
+          float f[8];
+          unpack8(ldcg16(xr + c), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot = fmaf(f[e], f[e], tot);
+        }
+      }
+      tot = warp_sum_xor(tot);
+      if (lane == 0) scale_s[t] = ref_mean_rsqrt(tot, K, a.eps);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int t = nt * 8 + g;
+      if (t < T) xsc[nt] = scale_s[t];
+    }
+  }
   for (int tile = 0; tile < n_tiles; ++tile) {
 #pragma unroll
     for (int m = 0; m < NM; ++m)
@@ -456,6 +467,8 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
   float* sc1 = sc0 + p.max_seq;
   float* qs = sc1 + p.max_seq;                           // [2][128] rotated queries (bf16 values)
   float* red = qs + 256;                                 // [16][2][128]
+  bf16* kcur = reinterpret_cast<bf16*>(red + 16 * 2 * 128);   // [128] this token's rotated K row
+  bf16* vcur = kcur + 128;                                     // [128] this token's V row
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nh = p.heads + 2 * p.kv_heads;
   const float scale = rbf(0.08838834764831845f);
@@ -467,6 +480,13 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
       const int t = b * p.S + s;
       const int pos = (p.pos_base ? __ldcg(p.pos_base + b) : 0) + p.pos_add + s;
       const int L = pos + 1;
+      // Rows j < pos are already in the cache: start this warp's first K and V loads now, so they travel
+      // together with the qkv loads below instead of one L2 round trip after another.
+      uint2 kpre = make_uint2(0u, 0u), vpre = make_uint2(0u, 0u);
+      if (warp < pos) {
+        kpre = __ldcg(reinterpret_cast<const uint2*>(kbase + (size_t)warp * 128 + 4 * lane));
+        vpre = __ldcg(reinterpret_cast<const uint2*>(vbase + (size_t)warp * 128 + 4 * lane));
+      }
       // warps 0,1: q heads 2kvh, 2kvh+1; warp 2: k; warp 3: v
       if (warp < 4) {
         const int hh = warp < 2 ? 2 * kvh + warp : (warp == 2 ? p.heads + kvh : p.heads + p.kv_heads + kvh);
@@ -476,7 +496,10 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
         for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(((uint32_t)__ldcg(src + lane + 32 * i)) << 16);
         if (warp == 3) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) vbase[(size_t)pos * 128 + lane + 32 * i] = f2bf(v[i]);
+          for (int i = 0; i < 4; ++i) {
+            vbase[(size_t)pos * 128 + lane + 32 * i] = f2bf(v[i]);
+            vcur[lane + 32 * i] = f2bf(v[i]);
+          }
         } else {
           const bf16* nw = warp < 2 ? p.q_norm_w : p.k_norm_w;
           float tmp = 0.f;
@@ -499,16 +522,35 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
             for (int i = 0; i < 4; ++i) qs[warp * 128 + lane + 32 * i] = o[i];
           } else {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) kbase[(size_t)pos * 128 + lane + 32 * i] = f2bf(o[i]);
+            for (int i = 0; i < 4; ++i) {
+              kbase[(size_t)pos * 128 + lane + 32 * i] = f2bf(o[i]);
+              kcur[lane + 32 * i] = f2bf(o[i]);
+            }
           }
         }
       }
-      __syncthreads();      // q in smem; this block's own K/V writes are visible to the block
+      __syncthreads();      // q, kcur, vcur in smem
       float q0[4], q1[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { q0[i] = qs[4 * lane + i]; q1[i] = qs[128 + 4 * lane + i]; }
-      for (int j = warp; j < L; j += MEGA_WARPS) {
-        const uint2 u = __ldcg(reinterpret_cast<const uint2*>(kbase + (size_t)j * 128 + 4 * lane));
+      // row j of K or V: the prefetched register (first iteration), the cache (j < pos) or this token (j == pos)
+      auto row = [&](const bf16* base, const bf16* cur, const uint2& pre, int j) -> uint2 {
+        if (j == pos) return *reinterpret_cast<const uint2*>(cur + 4 * lane);
+        if (j == warp) return pre;
+        return __ldcg(reinterpret_cast<const uint2*>(base + (size_t)j * 128 + 4 * lane));
+      };
+      for (int j0 = warp; j0 < L; j0 += 4 * MEGA_WARPS) {
+        uint2 ku[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + q * MEGA_WARPS;
+          ku[q] = j < L ? row(kbase, kcur, kpre, j) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q * MEGA_WARPS;
+        if (j >= L) break;
+        const uint2 u = ku[q];
         const float k0 = bf_lo(u.x), k1 = bf_hi(u.x), k2 = bf_lo(u.y), k3 = bf_hi(u.y);
         float d0 = q0[0] * k0 + q0[1] * k1 + q0[2] * k2 + q0[3] * k3;
         float d1 = q1[0] * k0 + q1[1] * k1 + q1[2] * k2 + q1[3] * k3;
@@ -517,6 +559,7 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
         if (lane == 0) {
           sc0[j] = rbf(rbf(d0) * scale);
           sc1[j] = rbf(rbf(d1) * scale);
+        }
         }
       }
       __syncthreads();
@@ -536,12 +579,23 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
       }
       __syncthreads();
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int j = warp; j < L; j += MEGA_WARPS) {
-        const uint2 u = __ldcg(reinterpret_cast<const uint2*>(vbase + (size_t)j * 128 + 4 * lane));
+      for (int j0 = warp; j0 < L; j0 += 4 * MEGA_WARPS) {
+        uint2 vu[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = j0 + q * MEGA_WARPS;
+          vu[q] = j < L ? row(vbase, vcur, vpre, j) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+        const int j = j0 + q * MEGA_WARPS;
+        if (j >= L) break;
+        const uint2 u = vu[q];
         const float v0 = bf_lo(u.x), v1 = bf_hi(u.x), v2 = bf_lo(u.y), v3 = bf_hi(u.y);
         const float p0 = sc0[j], p1 = sc1[j];
         o0[0] = fmaf(p0, v0, o0[0]); o0[1] = fmaf(p0, v1, o0[1]); o0[2] = fmaf(p0, v2, o0[2]); o0[3] = fmaf(p0, v3, o0[3]);
         o1[0] = fmaf(p1, v0, o1[0]); o1[1] = fmaf(p1, v1, o1[1]); o1[2] = fmaf(p1, v2, o1[2]); o1[3] = fmaf(p1, v3, o1[3]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -771,6 +825,6 @@ static size_t mega_smem_bytes(const q3_model_desc& d, int B, int max_seq, int gr
   if (!ok) return 0;
   size_t m = sizeof(SampleSmem);
   m = std::max(m, (size_t)(MEGA_TMAX + MEGA_MAX_TILES * 16 * MEGA_TMAX) * 4 + red_max);
-  m = std::max(m, (size_t)(2 * std::max(max_seq, d.cp_max_seq) + 256 + 16 * 2 * 128) * 4);
+  m = std::max(m, (size_t)(2 * std::max(max_seq, d.cp_max_seq) + 256 + 16 * 2 * 128) * 4 + 2 * 128 * 2);
   return m;
 }

@@ -62,7 +62,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 // smem: Bs_hi/Bs_lo [MC_BN + halo][MC_PITCH] bf16 ; As_hi/As_lo [2 stages][MC_BM][MC_PITCH] bf16
-__global__ void __launch_bounds__(256) voc_conv_mma_kernel(const MmaConvArgs a) {
+__global__ void __launch_bounds__(256, 2) voc_conv_mma_kernel(const MmaConvArgs a) {
   extern __shared__ __align__(16) unsigned char mc_smem[];
   const int halo = a.max_shift - a.min_shift;
   const int brows = MC_BN + halo;
