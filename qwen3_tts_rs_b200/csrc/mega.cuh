@@ -59,7 +59,9 @@ struct MegaArgs {
   unsigned long long* prof;     // optional: %globaltimer stamps of block 0 (tools/profile_mega.py)
   int prof_cap;
   int bar_mode;                 // 0: release-reduction + acquire spin; 1: fence + atomic + volatile spin
-  int prefetch_mode;            // 0: none, 1: own rows at phase start, 2: own + next phase's rows
+  int prefetch_mode;            // 0: none, 1: own rows at phase start, 2: own + next phase's rows (bulk, thread 0),
+                                // 3: next phase's rows only (bulk, thread 0, phase end), 4: next phase's rows, one
+                                // prefetch.global.L2 per 128-byte line spread over all threads, right after the loads are issued
   int bench_barriers;           // > 0: run only this many grid barriers (micro-benchmark)
   int dbg;                      // timing experiments only: 1 skip weight loads, 2 skip X loads, 4 skip combine, 8 skip MMA
 };
@@ -99,6 +101,36 @@ __device__ __forceinline__ void grid_sync(GridBar& gb) {
     } else {
       __threadfence();
       atomicAdd(gb.ctr, 1u);
+      while (*((volatile unsigned*)gb.ctr) < target) {
+      }
+      __threadfence();
+    }
+  }
+  gb.epoch += 1u;
+  __syncthreads();
+}
+// Split form.  Every phase ENDS with `__syncthreads(); grid_arrive(gb);` and BEGINS with grid_wait(gb) -- placed after
+// whatever the phase can do without the other CTAs' results (descriptor set-up, and in the skinny-GEMM phases the
+// first weight and residual loads, which then travel while the CTA waits).  The kernel posts one arrive up front.
+__device__ __forceinline__ void grid_arrive(GridBar& gb) {
+  if (threadIdx.x == 0) {
+    if (gb.mode == 0) {
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(gb.ctr) : "memory");
+    } else {
+      __threadfence();
+      atomicAdd(gb.ctr, 1u);
+    }
+  }
+}
+__device__ __forceinline__ void grid_wait(GridBar& gb) {
+  if (threadIdx.x == 0) {
+    const unsigned target = (gb.epoch + 1u) * gridDim.x;
+    if (gb.mode == 0) {
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gb.ctr) : "memory");
+      } while (v < target);
+    } else {
       while (*((volatile unsigned*)gb.ctr) < target) {
       }
       __threadfence();
@@ -154,9 +186,11 @@ struct GemvP {
 };
 
 // Contiguous 8-row units dealt evenly to the CTAs: CTA c owns rows [r0, r1).
+// c_grid_magic = ceil(2^24 / gridDim.x): exact quotient for units * gridDim.x < 2^24 (units <= 768 here).
+__constant__ unsigned c_grid_magic;
 __device__ __forceinline__ void mega_row_range(int N, int& r0, int& r1) {
   const int units = N >> 3, G = gridDim.x, c = blockIdx.x;
-  const int base = units / G, rem = units - base * G;
+  const int base = (int)(((unsigned)units * c_grid_magic) >> 24), rem = units - base * G;   // units / G without a divide
   const int u0 = c * base + min(c, rem);
   r0 = u0 << 3;
   r1 = (u0 + base + (c < rem ? 1 : 0)) << 3;
@@ -172,12 +206,28 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, size_t bytes) {
   }
 }
 __device__ __forceinline__ void mega_prefetch_rows(const bf16* W, const bf16* W2, int N, int K) {
-  if (W == nullptr || threadIdx.x != 0) return;
+  if (W == nullptr || threadIdx.x != 32) return;     // warp 1: thread 0 is busy with the barrier and the next descriptor
   int r0, r1;
   mega_row_range(N, r0, r1);
   if (r1 <= r0) return;
   l2_prefetch_bulk(W + (size_t)r0 * K, (size_t)(r1 - r0) * K * 2);
   if (W2 != nullptr) l2_prefetch_bulk(W2 + (size_t)r0 * K, (size_t)(r1 - r0) * K * 2);
+}
+
+// Same rows, one prefetch.global.L2 per 128-byte line, spread over the whole CTA (no thread is held up by the
+// bulk-copy engine's issue cost).
+__device__ __forceinline__ void mega_prefetch_lines(const bf16* W, const bf16* W2, int N, int K) {
+  if (W == nullptr) return;
+  int r0, r1;
+  mega_row_range(N, r0, r1);
+  if (r1 <= r0) return;
+  const size_t bytes = (size_t)(r1 - r0) * K * 2;
+  const char* b0 = reinterpret_cast<const char*>(W + (size_t)r0 * K);
+  const char* b1 = W2 ? reinterpret_cast<const char*>(W2 + (size_t)r0 * K) : nullptr;
+  for (size_t o = (size_t)threadIdx.x * 128; o < bytes; o += (size_t)MEGA_THREADS * 128) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(b0 + o));
+    if (b1) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + o));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -190,7 +240,7 @@ __device__ __forceinline__ void mega_prefetch_rows(const bf16* W, const bf16* W2
 // keeps integer divisions and predicated zero-fills off the common path.
 // smem: scale[16] | sqbuf [64 rows][16] | red [tile][16 warps][NT][NM][16][8] f32
 template <bool DUAL, int NT, bool NORM>
-__device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsigned char* smem) {
+__device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsigned char* smem, GridBar& gb) {
   float* scale_s = reinterpret_cast<float*>(smem);
   float* sqbuf = scale_s + MEGA_TMAX;                       // [MEGA_MAX_TILES*16 rows][MEGA_TMAX] squares for ss_out
   float* red = sqbuf + MEGA_MAX_TILES * 16 * MEGA_TMAX;     // partial sums
@@ -199,37 +249,18 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
   int r0, r1;
   mega_row_range(p.N, r0, r1);
   if (r1 <= r0) {                                    // no rows here (block 0 always owns rows)
+    grid_wait(gb);
     if (p.ss_out != nullptr && tid < MEGA_TMAX) p.ss_out[blockIdx.x * MEGA_TMAX + tid] = 0.f;
-    if (a.prefetch_mode >= 2) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+    __syncthreads();
+    grid_arrive(gb);
+    if (a.prefetch_mode == 2 || a.prefetch_mode == 3) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+    if (a.prefetch_mode == 4) mega_prefetch_lines(p.next_W, p.next_W2, p.next_N, p.next_K);
     return;
   }
-  if (a.prefetch_mode >= 1) mega_prefetch_rows(p.W, p.W2, p.N, K);
+  if (a.prefetch_mode == 1 || a.prefetch_mode == 2) mega_prefetch_rows(p.W, p.W2, p.N, K);
   prof_stamp(a, 1);
-  prof_stamp(a, 2);
-  // this lane's activation rows: token nt*8 + g of each n-tile
   const bf16* xrow[NT];
   float xsc[NT];
-#pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
-    const int t = nt * 8 + g;
-    xrow[nt] = nullptr;
-    xsc[nt] = 0.f;
-    if (t < T) {
-      if (p.xmode == X_CP0) {
-        const int b = t >> 1;
-        xrow[nt] = (t & 1) ? p.emb + (size_t)__ldcg(a.fs.cur_tok + b) * K : a.fs.last_hidden + (size_t)b * K;
-      } else if (p.xmode == X_CPG) {
-        xrow[nt] = p.emb + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + t)) * K;
-      } else {
-        xrow[nt] = p.X + (size_t)t * p.ldx;
-      }
-    }
-  }
-  if (blockIdx.x == 0) {
-    if (p.xmode == X_CPG && tid < T)
-      a.fs.frame_codes[tid * 16 + p.g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + tid));
-    if (p.xmode == X_CP0 && tid < a.B) a.fs.frame_codes[tid * 16] = __ldcg(a.fs.cur_tok + tid);
-  }
   const bool write_xn = NORM && p.xn_out != nullptr && blockIdx.x == 0;
   const int ksteps = K >> 5;                         // 32 k per step; warp w owns k-steps w, w+16, w+32, ...
   constexpr int NM = DUAL ? 2 : 1;
@@ -242,21 +273,21 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
 
   // residual inputs of the epilogue, fetched now so their L2 latency hides behind the weight stream.
   // Combine mapping: output idx = tid + it*512 -> token t = idx >> 6, CTA-local row = idx & 63.
-  float rpre[MEGA_MAX_OUT];
+  unsigned short rraw[MEGA_MAX_OUT];                 // raw bf16 bits; converted where they are used
 #pragma unroll
   for (int it = 0; it < MEGA_MAX_OUT; ++it) {
-    rpre[it] = 0.f;
+    rraw[it] = 0;
     const int idx = tid + it * MEGA_THREADS;
     const int t = idx >> 6, n = r0 + (idx & 63);
-    if ((p.epi == EPI_RESIDUAL || p.epi == EPI_O_H1) && t < T && n < r1) rpre[it] = ldcg_bf16(p.R + (size_t)t * p.ldr + n);
+    if ((p.epi == EPI_RESIDUAL || p.epi == EPI_O_H1) && t < T && n < r1)
+      rraw[it] = __ldcg(reinterpret_cast<const unsigned short*>(p.R + (size_t)t * p.ldr + n));
   }
 
   uint4 wl[NM][JU], wh[NM][JU], xv[NT][JU], wn[JU];
-  auto load_chunk = [&](int tile, int c) {
+  auto load_w = [&](int tile, int c) {
     const int n0 = r0 + (tile << 4);
     const bool hi_ok = (n0 + 8) < r1;
     const size_t woff = (size_t)(n0 + g) * K + koff0 + (size_t)c * (JU * 512);
-    const int xo = koff0 + c * (JU * 512);
     if (k_full && hi_ok) {                           // common path: no predication, no zero fill
 #pragma unroll
       for (int u = 0; u < JU; ++u) {
@@ -284,6 +315,9 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
         }
       }
     }
+  };
+  auto load_x = [&](int c) {
+    const int xo = koff0 + c * (JU * 512);
 #pragma unroll
     for (int u = 0; u < JU; ++u) {
       const bool ok = k_full || (c * JU + u) < jn;
@@ -299,7 +333,34 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
     }
   };
   float acc[NM][NT][4];
-  load_chunk(0, 0);
+  // ---- before the barrier: the first weights (and the residual rows above) do not depend on the previous phase ----
+  load_w(0, 0);
+  grid_wait(gb);
+  prof_stamp(a, 2);
+  // this lane's activation rows: token nt*8 + g of each n-tile
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int t = nt * 8 + g;
+    xrow[nt] = nullptr;
+    xsc[nt] = 0.f;
+    if (t < T) {
+      if (p.xmode == X_CP0) {
+        const int b = t >> 1;
+        xrow[nt] = (t & 1) ? p.emb + (size_t)__ldcg(a.fs.cur_tok + b) * K : a.fs.last_hidden + (size_t)b * K;
+      } else if (p.xmode == X_CPG) {
+        xrow[nt] = p.emb + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + t)) * K;
+      } else {
+        xrow[nt] = p.X + (size_t)t * p.ldx;
+      }
+    }
+  }
+  if (blockIdx.x == 0) {
+    if (p.xmode == X_CPG && tid < T)
+      a.fs.frame_codes[tid * 16 + p.g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + tid));
+    if (p.xmode == X_CP0 && tid < a.B) a.fs.frame_codes[tid * 16] = __ldcg(a.fs.cur_tok + tid);
+  }
+  load_x(0);
+  if (a.prefetch_mode == 4) mega_prefetch_lines(p.next_W, p.next_W2, p.next_N, p.next_K);
   if (NORM) {
     // row scales, computed while the first chunk's loads are in flight: one warp per token
     for (int t = warp; t < T; t += MEGA_WARPS) {
@@ -332,6 +393,7 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
       if (t < T) xsc[nt] = scale_s[t];
     }
   }
+  prof_stamp(a, 6);
   for (int tile = 0; tile < n_tiles; ++tile) {
 #pragma unroll
     for (int m = 0; m < NM; ++m)
@@ -364,8 +426,8 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
       }
       // the registers are free again: put the next chunk (possibly of the next tile) in flight right away, so it
       // overlaps the cross-warp combine below
-      if (c + 1 < n_chunks) load_chunk(tile, c + 1);
-      else if (tile + 1 < n_tiles) load_chunk(tile + 1, 0);
+      if (c + 1 < n_chunks) { load_w(tile, c + 1); load_x(c + 1); }
+      else if (tile + 1 < n_tiles) { load_w(tile + 1, 0); load_x(0); }
     }
     // this tile's partial sums -> shared memory (combined for all tiles at once below)
 #pragma unroll
@@ -377,7 +439,9 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
         *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * tg) = make_float2(acc[m][nt][2], acc[m][nt][3]);
       }
   }
+  prof_stamp(a, 7);
   __syncthreads();
+  prof_stamp(a, 8);
   // ---- fixed-order combine + epilogue for every (token, CTA-local row), spread over all 512 threads ----
 #pragma unroll
   for (int it = 0; it < MEGA_MAX_OUT; ++it) {
@@ -403,12 +467,12 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
           sq = y * y;
         } break;
         case EPI_RESIDUAL: {
-          const float y = rbf(rpre[it] + v);
+          const float y = rbf(__uint_as_float(((uint32_t)rraw[it]) << 16) + v);
           p.Y[(size_t)t * p.ldy + n] = f2bf(y);
           sq = y * y;             // the next layer's input_layernorm reads the stored (rounded) tensor
         } break;
         case EPI_O_H1: {
-          const float su = rpre[it] + v;                                     // x + attn_out, un-rounded f32
+          const float su = __uint_as_float(((uint32_t)rraw[it]) << 16) + v;                                     // x + attn_out, un-rounded f32
           p.Y[(size_t)t * p.ldy + n] = f2bf(su);                            // h1: the rounded sum
           sq = su * su;           // fused_residual_rmsnorm.cu:60-65: sum of squares of the UN-rounded sum
         } break;
@@ -435,19 +499,20 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
     }
   }
   __syncthreads();
+  grid_arrive(gb);
   prof_stamp(a, 3);
-  if (a.prefetch_mode >= 2) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+  if (a.prefetch_mode == 2 || a.prefetch_mode == 3) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
 }
 
 template <bool DUAL>
-__device__ __forceinline__ void mega_gemv(const MegaArgs& a, const GemvP& p, unsigned char* smem) {
+__device__ __forceinline__ void mega_gemv(const MegaArgs& a, const GemvP& p, unsigned char* smem, GridBar& gb) {
   const bool norm = p.xmode == X_NORM;
   if (p.T <= 8) {
-    if (norm) mega_gemv_t<DUAL, 1, true>(a, p, smem);
-    else mega_gemv_t<DUAL, 1, false>(a, p, smem);
+    if (norm) mega_gemv_t<DUAL, 1, true>(a, p, smem, gb);
+    else mega_gemv_t<DUAL, 1, false>(a, p, smem, gb);
   } else {
-    if (norm) mega_gemv_t<DUAL, 2, true>(a, p, smem);
-    else mega_gemv_t<DUAL, 2, false>(a, p, smem);
+    if (norm) mega_gemv_t<DUAL, 2, true>(a, p, smem, gb);
+    else mega_gemv_t<DUAL, 2, false>(a, p, smem, gb);
   }
 }
 
@@ -619,7 +684,9 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
 // Phase descriptors live in SHARED memory: thread 0 fills them, everybody reads them (broadcast).  Building
 // them per thread on the stack would cost ~150 B of local-memory traffic per thread per phase (6 GB of DRAM
 // writes per frame at 75 k threads x 546 phases -- measured with ncu before this change).
+constexpr int MEGA_MAX_LAYERS = 40;
 struct MegaShared {
+  LayerW layers[MEGA_MAX_LAYERS];   // talker layers then code-predictor layers (pointer tables read by every descriptor fill)
   MegaArgs a;
   GemvP gp;
   AttnP ap;
@@ -646,8 +713,7 @@ __device__ __noinline__ void mega_layers(MegaShared& sh, const MegaStack& st, in
       q.epi = EPI_STORE; q.Y = a.qkv; q.ldy = nh * 128;
       q.next_W = wp->wo; q.next_N = st.H; q.next_K = st.heads * 128;
     MEGA_FILL_END()
-    mega_gemv<false>(a, sh.gp, smem);
-    grid_sync(gb);
+    mega_gemv<false>(a, sh.gp, smem, gb);
     // P2: QK-norm, RoPE, KV append, attention
     if (threadIdx.x == 0) {
       AttnP& at = sh.ap;
@@ -655,27 +721,26 @@ __device__ __noinline__ void mega_layers(MegaShared& sh, const MegaStack& st, in
       at.q_norm_w = wp->q_norm; at.k_norm_w = wp->k_norm; at.cos_tab = cos_tab; at.sin_tab = sin_tab; at.pos_base = pos_base;
       at.pos_add = pos_add; at.S = S; at.B = a.B; at.heads = st.heads; at.kv_heads = st.kv_heads; at.max_seq = cache_seq;
     }
-    __syncthreads();
+    grid_wait(gb);
     prof_stamp(a, 4);
     mega_attn(a, sh.ap, smem);
+    __syncthreads();
+    grid_arrive(gb);
     prof_stamp(a, 5);
-    grid_sync(gb);
     // P3: o_proj + residual: h1 = bf16(x + attn_out), partial sum of squares of the un-rounded sum
     MEGA_FILL_BEGIN(sh)
       q.W = wp->wo; q.N = st.H; q.K = st.heads * 128; q.T = T; q.xmode = X_PLAIN; q.X = a.attn; q.ldx = st.heads * 128;
       q.epi = EPI_O_H1; q.R = a.x; q.ldr = st.H; q.Y = a.h1; q.ldy = st.H; q.ss_out = a.ssA;
       q.next_W = wp->gate; q.next_W2 = wp->up; q.next_N = st.I; q.next_K = st.H;
     MEGA_FILL_END()
-    mega_gemv<false>(a, sh.gp, smem);
-    grid_sync(gb);
+    mega_gemv<false>(a, sh.gp, smem, gb);
     // P4: post-attention RMSNorm (scale from P3's partials, applied to the rounded h1) -> SwiGLU(gate, up)
     MEGA_FILL_BEGIN(sh)
       q.W = wp->gate; q.W2 = wp->up; q.N = st.I; q.K = st.H; q.T = T; q.xmode = X_NORM; q.X = a.h1; q.ldx = st.H;
       q.norm_w = wp->post_ln; q.ss_in = a.ssA; q.epi = EPI_SWIGLU; q.Y = a.act; q.ldy = st.I;
       q.next_W = wp->down; q.next_N = st.H; q.next_K = st.I;
     MEGA_FILL_END()
-    mega_gemv<true>(a, sh.gp, smem);
-    grid_sync(gb);
+    mega_gemv<true>(a, sh.gp, smem, gb);
     // P5: down_proj + residual -> x
     MEGA_FILL_BEGIN(sh)
       q.W = wp->down; q.N = st.H; q.K = st.I; q.T = T; q.xmode = X_PLAIN; q.X = a.act; q.ldx = st.I;
@@ -686,8 +751,7 @@ __device__ __noinline__ void mega_layers(MegaShared& sh, const MegaStack& st, in
         q.next_W = after_W; q.next_N = after_N; q.next_K = after_K;
       }
     MEGA_FILL_END()
-    mega_gemv<false>(a, sh.gp, smem);
-    grid_sync(gb);
+    mega_gemv<false>(a, sh.gp, smem, gb);
   }
 }
 
@@ -708,6 +772,18 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.a);
     for (int i = threadIdx.x; i < (int)(sizeof(MegaArgs) / 4); i += MEGA_THREADS) dst[i] = src[i];
     if (threadIdx.x == 0) s_prof_idx = g_prof_idx;
+    const int nl = args.tk.n_layers + args.cp.n_layers;
+    const uint32_t* l0 = reinterpret_cast<const uint32_t*>(args.tk.layers);
+    const uint32_t* l1 = reinterpret_cast<const uint32_t*>(args.cp.layers);
+    uint32_t* ld = reinterpret_cast<uint32_t*>(sh.layers);
+    constexpr int W4 = (int)(sizeof(LayerW) / 4);
+    for (int i = threadIdx.x; i < nl * W4; i += MEGA_THREADS)
+      ld[i] = i < args.tk.n_layers * W4 ? l0[i] : l1[i - args.tk.n_layers * W4];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sh.a.tk.layers = sh.layers;
+    sh.a.cp.layers = sh.layers + sh.a.tk.n_layers;
   }
   __syncthreads();
   const MegaArgs& a = sh.a;
@@ -717,11 +793,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
     for (int i = 0; i < a.bench_barriers; ++i) grid_sync(gb);
     return;
   }
+  grid_arrive(gb);                 // every phase waits for its predecessor's arrive; this is the first phase's
   for (int frame = 0; frame < a.n_frames; ++frame) {
+    {
+      // frame prologue (its own phase): the previous frame's sampler is complete from here on
+      grid_wait(gb);
+      if (frame > 0 && a.do_sample) {
+        // stop early once every row has sampled EOS (uniform decision: all CTAs read the same flags)
+        int active = 0;
+        for (int b = 0; b < B; ++b) active += __ldcg(a.fs.done + b) ? 0 : 1;
+        if (active == 0) break;
+      }
+      if (a.do_cp && blockIdx.x == 0)
+        for (int i = threadIdx.x; i < a.n_ac * B; i += MEGA_THREADS) a.fs.amax[i] = 0ull;
+      __syncthreads();
+      grid_arrive(gb);
+    }
     if (a.do_cp) {
       // ---- code predictor: 15 dependent passes (code_predictor.rs:320-416) ----
-      if (blockIdx.x == 0)
-        for (int i = threadIdx.x; i < a.n_ac * B; i += MEGA_THREADS) a.fs.amax[i] = 0ull;
       const int nh_cp = (a.cp.heads + 2 * a.cp.kv_heads) * 128;
       for (int g = 0; g < a.n_ac; ++g) {
         const int T = g == 0 ? 2 * B : B, S = g == 0 ? 2 : 1;
@@ -732,8 +821,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
           q.next_W = a.cp.layers[0].wqkv; q.next_N = nh_cp; q.next_K = a.C;
         MEGA_FILL_END()
         if (a.cp_proj_w) {
-          mega_gemv<false>(a, sh.gp, mega_smem);
-        } else if (blockIdx.x == 0) {
+          mega_gemv<false>(a, sh.gp, mega_smem, gb);
+        } else {
+          grid_wait(gb);
+          if (blockIdx.x == 0) {
           // no projection (talker hidden == CP hidden): the gathered rows are the layer input
           const int K8 = a.H >> 3;
           for (int i = threadIdx.x; i < T * K8; i += MEGA_THREADS) {
@@ -750,8 +841,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
           if (g == 0) { if (threadIdx.x < B) a.fs.frame_codes[threadIdx.x * 16] = __ldcg(a.fs.cur_tok + threadIdx.x); }
           else if (threadIdx.x < B)
             a.fs.frame_codes[threadIdx.x * 16 + g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + threadIdx.x));
+          }
+          __syncthreads();
+          grid_arrive(gb);
         }
-        grid_sync(gb);
         mega_layers(sh, a.cp, T, S, nullptr, g == 0 ? 0 : g + 1, a.cp_k, a.cp_v, a.cp_max_seq, a.cp_cos, a.cp_sin, mega_smem,
                     a.cp_proj_w ? a.ssB : nullptr, a.cp_head[g], a.cpV, a.C, gb);
         MEGA_FILL_BEGIN(sh)
@@ -766,21 +859,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
             q.next_W = a.tk.layers[0].wqkv; q.next_N = (a.tk.heads + 2 * a.tk.kv_heads) * 128; q.next_K = a.H;
           }
         MEGA_FILL_END()
-        mega_gemv<false>(a, sh.gp, mega_smem);
-        grid_sync(gb);
+        mega_gemv<false>(a, sh.gp, mega_smem, gb);
       }
     }
     if (a.do_finish) {
       // ---- emit the frame, build the talker input (lib.rs:605-622) ----
+      grid_wait(gb);
       mega_finish(a, sh.codes);
-      grid_sync(gb);
+      __syncthreads();
+      grid_arrive(gb);
     }
     if (a.do_talker) {
       // ---- talker step (talker.rs:716-736) ----
       const bf16* in = a.do_finish ? a.step_input : a.ext_step_input;
+      grid_wait(gb);
       for (int i = blockIdx.x * MEGA_THREADS + threadIdx.x; i < B * (a.H >> 3); i += gridDim.x * MEGA_THREADS)
         reinterpret_cast<uint4*>(a.x)[i] = ldcg16(reinterpret_cast<const uint4*>(in) + i);
-      grid_sync(gb);
+      __syncthreads();
+      grid_arrive(gb);
       mega_layers(sh, a.tk, B, 1, a.fs.offset, 0, a.tk_k, a.tk_v, a.max_seq, a.t_cos, a.t_sin, mega_smem, nullptr,
                   a.codec_head, a.V, a.H, gb);
       MEGA_FILL_BEGIN(sh)
@@ -792,18 +888,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
           else { q.next_W = a.cp.layers[0].wqkv; q.next_N = (a.cp.heads + 2 * a.cp.kv_heads) * 128; q.next_K = a.C; }
         }
       MEGA_FILL_END()
-      mega_gemv<false>(a, sh.gp, mega_smem);
-      grid_sync(gb);
+      mega_gemv<false>(a, sh.gp, mega_smem, gb);
     }
     if (a.do_sample) {
       // ---- penalties + sampling + state update (lib.rs:639-651) ----
       SampleSmem& sm = *reinterpret_cast<SampleSmem*>(mega_smem);
+      grid_wait(gb);
       for (int b = blockIdx.x; b < B; b += gridDim.x) mega_sample(a.smp, b, sm);
-      grid_sync(gb);
-      // stop early once every row has sampled EOS (uniform decision: all CTAs read the same flags)
-      int active = 0;
-      for (int b = 0; b < B; ++b) active += __ldcg(a.fs.done + b) ? 0 : 1;
-      if (active == 0) break;
+      __syncthreads();
+      grid_arrive(gb);
     }
   }
 }

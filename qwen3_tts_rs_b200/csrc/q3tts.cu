@@ -373,13 +373,15 @@ static MegaArgs mega_args(q3_session* s) {
   const char* e1 = std::getenv("Q3_BAR_MODE");
   const char* e2 = std::getenv("Q3_PREFETCH");
   a.bar_mode = e1 ? std::atoi(e1) : 0;
-  a.prefetch_mode = e2 ? std::atoi(e2) : 2;
+  a.prefetch_mode = e2 ? std::atoi(e2) : 3;
   const char* e3 = std::getenv("Q3_DBG");
   a.dbg = e3 ? std::atoi(e3) : 0;
   return a;
 }
 
 static void mega_launch(q3_session* s, MegaArgs& a) {
+  const unsigned magic = (unsigned)(((1ull << 24) + (unsigned)s->mega_grid - 1) / (unsigned)s->mega_grid);
+  Q3_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_grid_magic, &magic, 4, 0, cudaMemcpyHostToDevice, s->st));
   Q3_CHECK_CUDA(cudaMemsetAsync(s->bar.p, 0, 4, s->st));
   if (s->prof.p) { a.prof = s->prof.as<unsigned long long>(); a.prof_cap = (int)(s->prof.bytes / 8); }
   void* params[] = {(void*)&a};
@@ -768,7 +770,7 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
     s->mega_smem = mega_smem_bytes(d, B, max_seq, m->num_sms);
     s->bar.alloc(64);
     s->bar.zero();
-    if (want && 2 * B <= MEGA_TMAX && s->mega_smem > 0 && s->mega_smem <= 227 * 1024 && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 &&
+    if (want && 2 * B <= MEGA_TMAX && d.layers + d.cp_layers <= MEGA_MAX_LAYERS && s->mega_smem > 0 && s->mega_smem <= 227 * 1024 && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 &&
         d.inter % 32 == 0 && d.cp_inter % 32 == 0 && d.codec_vocab % 16 == 0 && d.cp_vocab % 16 == 0) {
       Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->mega_smem));
       int per_sm = 0;

@@ -29,31 +29,29 @@ L.check(lib.q3_debug_profile(sess.handle, a.frames, buf.ctypes.data_as(C.c_void_
 st = buf[: n.value]
 t = (st >> np.uint64(8)).astype(np.int64); tag = (st & np.uint64(0xff)).astype(int)
 print("stamps", n.value, "total us", (t[-1] - t[0]) / 1e3)
-# tags: 1 gemv entry, 2 after stage, 3 after tiles, 4 attn start, 5 attn end
-stage = tiles = attn = other = 0
-cnt = {1: 0, 4: 0}
+# tags: 1 gemv entry, 2 loads issued.., 6 first loads + scales done, 7 tile loop done, 8 combine barrier passed, 3 phase end, 4/5 attention
+seg = {}
+cnt = {}
+phases = []   # per gemv phase: dict of segment ns
+cur = None
 for i in range(1, len(t)):
-    d = t[i] - t[i - 1]
-    if tag[i - 1] == 1 and tag[i] == 2: stage += d; cnt[1] += 1
-    elif tag[i - 1] == 2 and tag[i] == 3: tiles += d
-    elif tag[i - 1] == 4 and tag[i] == 5: attn += d; cnt[4] += 1
-    else: other += d
-print(f"gemv phases {cnt[1]}: stage {stage/1e3:.1f} us ({stage/max(1,cnt[1]):.0f} ns each), tiles {tiles/1e3:.1f} us ({tiles/max(1,cnt[1]):.0f} ns each)")
-print(f"attn phases {cnt[4]}: {attn/1e3:.1f} us ({attn/max(1,cnt[4]):.0f} ns each); barriers+other {other/1e3:.1f} us ({other/max(1,cnt[1]+cnt[4]):.0f} ns per phase)")
-# first 40 deltas for a look at the CP pass 0 and talker layer 0
-print([(int(tag[i]), int(t[i] - t[i-1])) for i in range(1, min(60, len(t)))])
-# --- per-phase detail for one frame: list (stage_ns, tiles_ns) of consecutive gemv phases near the end (talker) and start (CP)
-ph = []
-i = 0
-while i < len(t) - 2:
-    if tag[i] == 1 and tag[i + 1] == 2 and tag[i + 2] == 3:
-        ph.append((int(t[i + 1] - t[i]), int(t[i + 2] - t[i + 1])))
-        i += 3
-    else:
-        i += 1
-per_frame = len(ph) // a.frames
+    d = int(t[i] - t[i - 1]); k = (int(tag[i - 1]), int(tag[i]))
+    seg[k] = seg.get(k, 0) + d; cnt[k] = cnt.get(k, 0) + 1
+    if tag[i - 1] == 1: cur = {}
+    if cur is not None:
+        cur[k] = d
+        if tag[i] == 3: phases.append(cur); cur = None
+for k in sorted(seg): print(f"  {k}: n={cnt[k]:5d} total {seg[k]/1e3:9.1f} us  mean {seg[k]/cnt[k]:7.0f} ns")
+per_frame = len(phases) // a.frames
 print("gemv phases per frame", per_frame)
-f0 = ph[:per_frame]
-print("CP pass 0 (proj, [qkv,o,gateup,down]x5, head) tiles ns:", [x[1] for x in f0[:22]])
-print("CP pass 1 tiles ns:", [x[1] for x in f0[22:44]])
-print("talker layers 0-1 (qkv,o,gateup,down) tiles ns:", [x[1] for x in f0[-113:-105]], " last layer+head:", [x[1] for x in f0[-5:]])
+names = ["proj"] + ["qkv", "o", "gateup", "down"] * 5 + ["head"]
+def show(label, ps, nm):
+    print(label)
+    for n_, p_ in zip(nm, ps):
+        print(f"   {n_:7s} load+scale {p_.get((2,6),0):6d}  tiles {p_.get((6,7),0):6d}  sync {p_.get((7,8),0):5d}  combine+epi {p_.get((8,3),0):6d}")
+f0 = phases[per_frame:2 * per_frame] if a.frames > 1 else phases[:per_frame]
+show("CP pass 0", f0[:22], names)
+show("CP pass 1", f0[22:44], names)
+show("CP pass 7", f0[22 * 7:22 * 8], names)
+show("talker layer 0-1", f0[-113:-105], ["qkv", "o", "gateup", "down"] * 2)
+show("talker last + head", f0[-5:], ["qkv", "o", "gateup", "down", "head"])
