@@ -32,6 +32,7 @@ constexpr int MEGA_THREADS = 512;
 constexpr int MEGA_WARPS = 16;
 constexpr int MEGA_TMAX = 16;       // tokens per phase (batch <= 8: the CP prefill pass has 2 tokens per row)
 constexpr int MEGA_MAX_TILES = 4;   // 16-row tiles per CTA per phase (N <= 4 * 16 * gridDim.x rows per matrix)
+constexpr int MEGA_SQ_STRIDE = 65;  // squares buffer [token][64 rows + 1]: conflict-free for row-wise writes and token-wise reads
 constexpr int MEGA_MAX_OUT = (MEGA_MAX_TILES * 16 * MEGA_TMAX + 511) / 512;   // outputs per thread in the combine
 
 struct MegaStack { const LayerW* layers; int n_layers, H, I, heads, kv_heads; };
@@ -63,7 +64,8 @@ struct MegaArgs {
                                 // 3: next phase's rows only (bulk, thread 0, phase end), 4: next phase's rows, one
                                 // prefetch.global.L2 per 128-byte line spread over all threads, right after the loads are issued
   int bench_barriers;           // > 0: run only this many grid barriers (micro-benchmark)
-  int dbg;                      // timing experiments only: 1 skip weight loads, 2 skip X loads, 4 skip combine, 8 skip MMA
+  int dbg;                      // unused
+  int small_mode;               // 1: phases whose weights fit in registers use mega_gemv_small (Q3_SMALL=0 turns it off)
 };
 
 __device__ unsigned int g_prof_idx;
@@ -214,6 +216,87 @@ __device__ __forceinline__ void mega_prefetch_rows(const bf16* W, const bf16* W2
   if (W2 != nullptr) l2_prefetch_bulk(W2 + (size_t)r0 * K, (size_t)(r1 - r0) * K * 2);
 }
 
+// Cross-warp combine (fixed order), fused epilogue, partial sums of squares, barrier arrive: the common tail of
+// the skinny-GEMM phases.  `red` holds the warps' partial sums as [nt][m][token col 0..7][warp][CTA-local row] f32
+// (column stride 16*R + 4 floats, R = 16 * n_tiles): the combine reads 32 consecutive rows per warp and the
+// fragment writes (lanes = 8 rows x 4 column pairs) hit 32 different banks -- both conflict-free.  (The first
+// layout, [tile][warp][nt][m][row][col], made every combine read an 8-way bank conflict: ~1 us per phase.)
+template <bool DUAL, int NT>
+__device__ __forceinline__ void mega_gemv_tail(const MegaArgs& a, const GemvP& p, float* red, float* sqbuf,
+                                               const unsigned short (&rraw)[MEGA_MAX_OUT], int r0, int r1, int n_tiles, int T,
+                                               GridBar& gb) {
+  constexpr int NM = DUAL ? 2 : 1;
+  const int tid = threadIdx.x;
+  const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
+  prof_stamp(a, 7);
+  __syncthreads();
+  prof_stamp(a, 8);
+  // ---- fixed-order combine + epilogue for every (token, CTA-local row), spread over all 512 threads ----
+#pragma unroll
+  for (int it = 0; it < MEGA_MAX_OUT; ++it) {
+    const int idx = tid + it * MEGA_THREADS;
+    const int t = idx >> 6, rem = idx & 63;
+    const int n = r0 + rem, nt = t >> 3, col = t & 7;
+    const bool valid = t < T && n < r1;
+    float sq = 0.f;             // contribution to the partial sum of squares of what the NEXT norm will see
+    if (valid) {
+      float v0 = 0.f, v1 = 0.f;
+      const float* rb = red + (size_t)((nt * NM) * 8 + col) * red_cs + rem;
+#pragma unroll
+      for (int w = 0; w < MEGA_WARPS; ++w) {
+        v0 += rb[w * red_r];
+        if (DUAL) v1 += rb[8 * red_cs + w * red_r];
+      }
+      const float v = rbf(v0);
+      switch (p.epi) {
+        case EPI_STORE: p.Y[(size_t)t * p.ldy + n] = f2bf(v); break;
+        case EPI_BIAS: {
+          const float y = rbf(v + bf2f(p.bias[n]));
+          p.Y[(size_t)t * p.ldy + n] = f2bf(y);
+          sq = y * y;
+        } break;
+        case EPI_RESIDUAL: {
+          const float y = rbf(__uint_as_float(((uint32_t)rraw[it]) << 16) + v);
+          p.Y[(size_t)t * p.ldy + n] = f2bf(y);
+          sq = y * y;             // the next layer's input_layernorm reads the stored (rounded) tensor
+        } break;
+        case EPI_O_H1: {
+          const float su = __uint_as_float(((uint32_t)rraw[it]) << 16) + v;                                     // x + attn_out, un-rounded f32
+          p.Y[(size_t)t * p.ldy + n] = f2bf(su);                            // h1: the rounded sum
+          sq = su * su;           // fused_residual_rmsnorm.cu:60-65: sum of squares of the UN-rounded sum
+        } break;
+        case EPI_SWIGLU: {
+          const float sg = rbf(silu_f(v));
+          p.Y[(size_t)t * p.ldy + n] = f2bf(sg * rbf(v1));
+        } break;
+        case EPI_LOGITS: {
+          if (p.Yf != nullptr) p.Yf[(size_t)t * p.N + n] = v;
+          if (p.amax != nullptr) atomicMax(p.amax + t, argmax_key(v, n));
+        } break;
+        default: break;
+      }
+    }
+    if (p.ss_out != nullptr && t < MEGA_TMAX) sqbuf[t * MEGA_SQ_STRIDE + rem] = sq;
+  }
+  if (p.ss_out != nullptr) {
+    __syncthreads();
+    const int w = tid >> 5, l = tid & 31;      // one warp per token sums its squares in a fixed order
+    if (w < MEGA_TMAX) {
+      float tot = 0.f;
+      if (w < T) {
+        const float s0 = l < red_r ? sqbuf[w * MEGA_SQ_STRIDE + l] : 0.f;
+        const float s1 = l + 32 < red_r ? sqbuf[w * MEGA_SQ_STRIDE + l + 32] : 0.f;
+        tot = warp_sum_xor(s0 + s1);
+      }
+      if (l == 0) p.ss_out[blockIdx.x * MEGA_TMAX + w] = tot;
+    }
+  }
+  __syncthreads();
+  grid_arrive(gb);
+  prof_stamp(a, 3);
+  if (a.prefetch_mode == 2 || a.prefetch_mode == 3) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+}
+
 // Same rows, one prefetch.global.L2 per 128-byte line, spread over the whole CTA (no thread is held up by the
 // bulk-copy engine's issue cost).
 __device__ __forceinline__ void mega_prefetch_lines(const bf16* W, const bf16* W2, int N, int K) {
@@ -243,7 +326,7 @@ template <bool DUAL, int NT, bool NORM>
 __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsigned char* smem, GridBar& gb) {
   float* scale_s = reinterpret_cast<float*>(smem);
   float* sqbuf = scale_s + MEGA_TMAX;                       // [MEGA_MAX_TILES*16 rows][MEGA_TMAX] squares for ss_out
-  float* red = sqbuf + MEGA_MAX_TILES * 16 * MEGA_TMAX;     // partial sums
+  float* red = sqbuf + MEGA_TMAX * MEGA_SQ_STRIDE;     // partial sums
   const int K = p.K, T = p.T;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   int r0, r1;
@@ -268,6 +351,7 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
   const int jn = ksteps > warp ? (ksteps - warp + MEGA_WARPS - 1) / MEGA_WARPS : 0;   // this warp's k-steps
   const int n_chunks = max(1, ((ksteps + MEGA_WARPS - 1) / MEGA_WARPS + JU - 1) / JU);   // uniform over warps
   const int n_tiles = (r1 - r0 + 15) >> 4;
+  const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;   // combine buffer strides (mega_gemv_tail)
   const int koff0 = warp * 32 + 8 * tg;              // element offset of this lane inside its first k-step
   const bool k_full = (ksteps % (MEGA_WARPS * JU)) == 0;   // every chunk of every warp is complete (all real models)
 
@@ -434,80 +518,222 @@ __device__ __noinline__ void mega_gemv_t(const MegaArgs& a, const GemvP& p, unsi
     for (int m = 0; m < NM; ++m)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        float* r = red + (((((size_t)tile * MEGA_WARPS + warp) * NT + nt) * NM + m) * 16) * 8;
-        *reinterpret_cast<float2*>(r + g * 8 + 2 * tg) = make_float2(acc[m][nt][0], acc[m][nt][1]);
-        *reinterpret_cast<float2*>(r + (g + 8) * 8 + 2 * tg) = make_float2(acc[m][nt][2], acc[m][nt][3]);
+        float* r = red + (size_t)((nt * NM + m) * 8 + 2 * tg) * red_cs + warp * red_r + (tile << 4) + g;
+        r[0] = acc[m][nt][0]; r[red_cs] = acc[m][nt][1]; r[8] = acc[m][nt][2]; r[red_cs + 8] = acc[m][nt][3];
       }
   }
-  prof_stamp(a, 7);
-  __syncthreads();
-  prof_stamp(a, 8);
-  // ---- fixed-order combine + epilogue for every (token, CTA-local row), spread over all 512 threads ----
+  mega_gemv_tail<DUAL, NT>(a, p, red, sqbuf, rraw, r0, r1, n_tiles, T, gb);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Small phases (every code-predictor phase, and the 0.6B talker): K == CHUNKS * 1024 and at most TILES 16-row tiles
+// per CTA, so ALL of a lane's weight fragments fit in registers (<= 16 x 128 bit).  They are requested before the
+// grid barrier; after it only the activations (L2) are fetched once, and every MMA of the phase follows without
+// another memory round trip.  Same fragment mapping, split-K and combine as mega_gemv_t -> same bits.
+template <bool DUAL, int NT, bool NORM, int TILES, int CHUNKS>
+__device__ __noinline__ void mega_gemv_small(const MegaArgs& a, const GemvP& p, unsigned char* smem, GridBar& gb) {
+  float* scale_s = reinterpret_cast<float*>(smem);
+  float* sqbuf = scale_s + MEGA_TMAX;
+  float* red = sqbuf + MEGA_TMAX * MEGA_SQ_STRIDE;
+  const int K = p.K, T = p.T;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+  constexpr int NM = DUAL ? 2 : 1;
+  constexpr int JU = 2;
+  int r0, r1;
+  mega_row_range(p.N, r0, r1);
+  if (r1 <= r0) {
+    grid_wait(gb);
+    if (p.ss_out != nullptr && tid < MEGA_TMAX) p.ss_out[blockIdx.x * MEGA_TMAX + tid] = 0.f;
+    __syncthreads();
+    grid_arrive(gb);
+    if (a.prefetch_mode == 2 || a.prefetch_mode == 3) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+    return;
+  }
+  prof_stamp(a, 1);
+  const int n_tiles = (r1 - r0 + 15) >> 4;
+  const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
+  const int koff0 = warp * 32 + 8 * tg;
+  unsigned short rraw[MEGA_MAX_OUT];
 #pragma unroll
   for (int it = 0; it < MEGA_MAX_OUT; ++it) {
+    rraw[it] = 0;
     const int idx = tid + it * MEGA_THREADS;
-    const int t = idx >> 6, rem = idx & 63, tile = rem >> 4, row = rem & 15;
-    const int n = r0 + rem, nt = t >> 3, col = t & 7;
-    const bool valid = t < T && n < r1;
-    float sq = 0.f;             // contribution to the partial sum of squares of what the NEXT norm will see
-    if (valid) {
-      float v0 = 0.f, v1 = 0.f;
-      const float* rb = red + ((((size_t)tile * MEGA_WARPS) * NT + nt) * NM * 16 + row) * 8 + col;
+    const int t = idx >> 6, n = r0 + (idx & 63);
+    if ((p.epi == EPI_RESIDUAL || p.epi == EPI_O_H1) && t < T && n < r1)
+      rraw[it] = __ldcg(reinterpret_cast<const unsigned short*>(p.R + (size_t)t * p.ldr + n));
+  }
+  // ---- before the barrier: every weight fragment of the phase ----
+  uint4 wl[TILES][CHUNKS][NM][JU], wh[TILES][CHUNKS][NM][JU];
 #pragma unroll
-      for (int w = 0; w < MEGA_WARPS; ++w) {
-        v0 += rb[(size_t)w * NT * NM * 128];
-        if (DUAL) v1 += rb[(size_t)w * NT * NM * 128 + 128];
+  for (int tile = 0; tile < TILES; ++tile) {
+    const int n0 = r0 + (tile << 4);
+    const bool lo_ok = tile < n_tiles, hi_ok = lo_ok && (n0 + 8) < r1;
+    const size_t woff = (size_t)(n0 + g) * K + koff0;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+      for (int u = 0; u < JU; ++u) {
+        const size_t o = woff + (size_t)c * (JU * 512) + u * 512;
+        wl[tile][c][0][u] = make_uint4(0, 0, 0, 0);
+        wh[tile][c][0][u] = make_uint4(0, 0, 0, 0);
+        if (lo_ok) wl[tile][c][0][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W + o));
+        if (hi_ok) wh[tile][c][0][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W + o + (size_t)8 * K));
+        if (DUAL) {
+          wl[tile][c][NM - 1][u] = make_uint4(0, 0, 0, 0);
+          wh[tile][c][NM - 1][u] = make_uint4(0, 0, 0, 0);
+          if (lo_ok) wl[tile][c][NM - 1][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W2 + o));
+          if (hi_ok) wh[tile][c][NM - 1][u] = ldg_stream(reinterpret_cast<const uint4*>(p.W2 + o + (size_t)8 * K));
+        }
       }
-      const float v = rbf(v0);
-      switch (p.epi) {
-        case EPI_STORE: p.Y[(size_t)t * p.ldy + n] = f2bf(v); break;
-        case EPI_BIAS: {
-          const float y = rbf(v + bf2f(p.bias[n]));
-          p.Y[(size_t)t * p.ldy + n] = f2bf(y);
-          sq = y * y;
-        } break;
-        case EPI_RESIDUAL: {
-          const float y = rbf(__uint_as_float(((uint32_t)rraw[it]) << 16) + v);
-          p.Y[(size_t)t * p.ldy + n] = f2bf(y);
-          sq = y * y;             // the next layer's input_layernorm reads the stored (rounded) tensor
-        } break;
-        case EPI_O_H1: {
-          const float su = __uint_as_float(((uint32_t)rraw[it]) << 16) + v;                                     // x + attn_out, un-rounded f32
-          p.Y[(size_t)t * p.ldy + n] = f2bf(su);                            // h1: the rounded sum
-          sq = su * su;           // fused_residual_rmsnorm.cu:60-65: sum of squares of the UN-rounded sum
-        } break;
-        case EPI_SWIGLU: {
-          const float sg = rbf(silu_f(v));
-          p.Y[(size_t)t * p.ldy + n] = f2bf(sg * rbf(v1));
-        } break;
-        case EPI_LOGITS: {
-          if (p.Yf != nullptr) p.Yf[(size_t)t * p.N + n] = v;
-          if (p.amax != nullptr) atomicMax(p.amax + t, argmax_key(v, n));
-        } break;
-        default: break;
+  }
+  grid_wait(gb);
+  prof_stamp(a, 2);
+  // ---- after the barrier: activations (once), scales ----
+  const bf16* xrow[NT];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const int t = nt * 8 + g;
+    xrow[nt] = nullptr;
+    if (t < T) {
+      if (p.xmode == X_CP0) {
+        const int b = t >> 1;
+        xrow[nt] = (t & 1) ? p.emb + (size_t)__ldcg(a.fs.cur_tok + b) * K : a.fs.last_hidden + (size_t)b * K;
+      } else if (p.xmode == X_CPG) {
+        xrow[nt] = p.emb + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + t)) * K;
+      } else {
+        xrow[nt] = p.X + (size_t)t * p.ldx;
       }
     }
-    if (p.ss_out != nullptr && t < MEGA_TMAX) sqbuf[rem * MEGA_TMAX + t] = sq;
   }
-  if (p.ss_out != nullptr) {
-    __syncthreads();
-    if (tid < MEGA_TMAX) {      // one thread per token sums its squares in a fixed order
+  if (blockIdx.x == 0) {
+    if (p.xmode == X_CPG && tid < T)
+      a.fs.frame_codes[tid * 16 + p.g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + tid));
+    if (p.xmode == X_CP0 && tid < a.B) a.fs.frame_codes[tid * 16] = __ldcg(a.fs.cur_tok + tid);
+  }
+  uint4 xv[CHUNKS][NT][JU];
+#pragma unroll
+  for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+    for (int u = 0; u < JU; ++u)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        xv[c][nt][u] = make_uint4(0, 0, 0, 0);
+        if (xrow[nt] != nullptr) xv[c][nt][u] = ldcg16(xrow[nt] + koff0 + c * (JU * 512) + u * 512);
+      }
+  if (NORM) {
+    for (int t = warp; t < T; t += MEGA_WARPS) {
       float tot = 0.f;
-      if (tid < T)
-        for (int r = 0; r < n_tiles * 16; ++r) tot += sqbuf[r * MEGA_TMAX + tid];
-      p.ss_out[blockIdx.x * MEGA_TMAX + tid] = tot;
+      if (p.ss_in != nullptr) {
+        float part[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const int c = lane + 32 * i;
+          part[i] = c < (int)gridDim.x ? __ldcg(p.ss_in + c * MEGA_TMAX + t) : 0.f;
+        }
+        tot = ((part[0] + part[1]) + (part[2] + part[3])) + part[4];
+        for (int c = lane + 160; c < (int)gridDim.x; c += 32) tot += __ldcg(p.ss_in + c * MEGA_TMAX + t);
+      } else {
+        const bf16* xr = p.X + (size_t)t * p.ldx;
+        for (int c = 8 * lane; c < K; c += 256) {
+          float f[8];
+          unpack8(ldcg16(xr + c), f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) tot = fmaf(f[e], f[e], tot);
+        }
+      }
+      tot = warp_sum_xor(tot);
+      if (lane == 0) scale_s[t] = ref_mean_rsqrt(tot, K, a.eps);
+    }
+    __syncthreads();
+    const bool write_xn = p.xn_out != nullptr && blockIdx.x == 0;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int t = nt * 8 + g;
+      const float sc = t < T ? scale_s[t] : 0.f;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+        for (int u = 0; u < JU; ++u) {
+          const int xo = koff0 + c * (JU * 512) + u * 512;
+          float f[8], w[8];
+          unpack8(xv[c][nt][u], f);
+          unpack8(*reinterpret_cast<const uint4*>(p.norm_w + xo), w);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = (sc * f[e]) * w[e];
+          xv[c][nt][u] = pack8(f);
+          if (write_xn && xrow[nt] != nullptr) *reinterpret_cast<uint4*>(p.xn_out + (size_t)t * K + xo) = xv[c][nt][u];
+        }
     }
   }
-  __syncthreads();
-  grid_arrive(gb);
-  prof_stamp(a, 3);
-  if (a.prefetch_mode == 2 || a.prefetch_mode == 3) mega_prefetch_rows(p.next_W, p.next_W2, p.next_N, p.next_K);
+  prof_stamp(a, 6);
+#pragma unroll
+  for (int tile = 0; tile < TILES; ++tile) {
+    if (tile < n_tiles) {
+      float acc[NM][NT][4];
+#pragma unroll
+      for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[m][nt][i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c)
+#pragma unroll
+        for (int u = 0; u < JU; ++u)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+              const uint4 x4 = xv[c][nt][u];
+              mma_bf16_16816(acc[m][nt], wl[tile][c][m][u].x, wh[tile][c][m][u].x, wl[tile][c][m][u].y, wh[tile][c][m][u].y, x4.x, x4.y);
+              mma_bf16_16816(acc[m][nt], wl[tile][c][m][u].z, wh[tile][c][m][u].z, wl[tile][c][m][u].w, wh[tile][c][m][u].w, x4.z, x4.w);
+            }
+#pragma unroll
+      for (int m = 0; m < NM; ++m)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float* r = red + (size_t)((nt * NM + m) * 8 + 2 * tg) * red_cs + warp * red_r + (tile << 4) + g;
+          r[0] = acc[m][nt][0]; r[red_cs] = acc[m][nt][1]; r[8] = acc[m][nt][2]; r[red_cs + 8] = acc[m][nt][3];
+        }
+    }
+  }
+  mega_gemv_tail<DUAL, NT>(a, p, red, sqbuf, rraw, r0, r1, n_tiles, T, gb);
 }
 
 template <bool DUAL>
 __device__ __forceinline__ void mega_gemv(const MegaArgs& a, const GemvP& p, unsigned char* smem, GridBar& gb) {
   const bool norm = p.xmode == X_NORM;
-  if (p.T <= 8) {
+  const bool nt1 = p.T <= 8;
+  // widest CTA of the phase (uniform over the grid): units per CTA -> tiles
+  const int units = p.N >> 3, base = (int)(((unsigned)units * c_grid_magic) >> 24);
+  const int max_tiles = (base + (units - base * (int)gridDim.x > 0 ? 1 : 0) + 1) >> 1;
+  if (a.small_mode != 0) {
+    if (DUAL) {
+      if (norm && p.K == 1024 && max_tiles <= 2) {
+        if (nt1) mega_gemv_small<DUAL, 1, true, 2, 1>(a, p, smem, gb);
+        else mega_gemv_small<DUAL, 2, true, 2, 1>(a, p, smem, gb);
+        return;
+      }
+    } else {
+      if (norm && p.K == 1024 && max_tiles <= 2) {
+        if (nt1) mega_gemv_small<false, 1, true, 2, 1>(a, p, smem, gb);
+        else mega_gemv_small<false, 2, true, 2, 1>(a, p, smem, gb);
+        return;
+      }
+      if (!norm && p.K == 2048 && max_tiles <= 1) {
+        if (nt1) mega_gemv_small<false, 1, false, 1, 2>(a, p, smem, gb);
+        else mega_gemv_small<false, 2, false, 1, 2>(a, p, smem, gb);
+        return;
+      }
+      if (!norm && p.K == 3072 && max_tiles <= 1) {
+        if (nt1) mega_gemv_small<false, 1, false, 1, 3>(a, p, smem, gb);
+        else mega_gemv_small<false, 2, false, 1, 3>(a, p, smem, gb);
+        return;
+      }
+    }
+  }
+  if (nt1) {
     if (norm) mega_gemv_t<DUAL, 1, true>(a, p, smem, gb);
     else mega_gemv_t<DUAL, 1, false>(a, p, smem, gb);
   } else {
@@ -527,6 +753,7 @@ struct AttnP {
   int pos_add, S, B, heads, kv_heads, max_seq;
 };
 
+constexpr int ATT_U = 8;   // cache rows per warp whose loads are in flight together
 __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsigned char* smem) {
   float* sc0 = reinterpret_cast<float*>(smem);          // [max_seq]
   float* sc1 = sc0 + p.max_seq;
@@ -604,15 +831,15 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
         if (j == warp) return pre;
         return __ldcg(reinterpret_cast<const uint2*>(base + (size_t)j * 128 + 4 * lane));
       };
-      for (int j0 = warp; j0 < L; j0 += 4 * MEGA_WARPS) {
-        uint2 ku[4];
+      for (int j0 = warp; j0 < L; j0 += ATT_U * MEGA_WARPS) {
+        uint2 ku[ATT_U];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < ATT_U; ++q) {
           const int j = j0 + q * MEGA_WARPS;
           ku[q] = j < L ? row(kbase, kcur, kpre, j) : make_uint2(0u, 0u);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < ATT_U; ++q) {
         const int j = j0 + q * MEGA_WARPS;
         if (j >= L) break;
         const uint2 u = ku[q];
@@ -644,15 +871,15 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
       }
       __syncthreads();
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int j0 = warp; j0 < L; j0 += 4 * MEGA_WARPS) {
-        uint2 vu[4];
+      for (int j0 = warp; j0 < L; j0 += ATT_U * MEGA_WARPS) {
+        uint2 vu[ATT_U];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < ATT_U; ++q) {
           const int j = j0 + q * MEGA_WARPS;
           vu[q] = j < L ? row(vbase, vcur, vpre, j) : make_uint2(0u, 0u);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < ATT_U; ++q) {
         const int j = j0 + q * MEGA_WARPS;
         if (j >= L) break;
         const uint2 u = vu[q];
@@ -910,14 +1137,14 @@ static size_t mega_smem_bytes(const q3_model_desc& d, int B, int max_seq, int gr
     const int units = N / 8, per_cta = (units + grid - 1) / grid, tiles = (per_cta + 1) / 2;
     if (tiles > MEGA_MAX_TILES || T > MEGA_TMAX || N % 8 != 0) ok = false;
     const int NT = (T + 7) / 8;
-    red_max = std::max(red_max, (size_t)tiles * 16 * NT * (dual ? 2 : 1) * 16 * 8 * 4);
+    red_max = std::max(red_max, (size_t)NT * (dual ? 2 : 1) * 8 * (256 * tiles + 4) * 4);
   };
   const int nh = (d.heads + 2 * d.kv_heads) * 128, cnh = (d.cp_heads + 2 * d.cp_kv_heads) * 128;
   phase(nh, B, false); phase(d.hidden, B, false); phase(d.inter, B, true); phase(d.codec_vocab, B, false);
   phase(d.cp_hidden, 2 * B, false); phase(cnh, 2 * B, false); phase(d.cp_inter, 2 * B, true); phase(d.cp_vocab, B, false);
   if (!ok) return 0;
   size_t m = sizeof(SampleSmem);
-  m = std::max(m, (size_t)(MEGA_TMAX + MEGA_MAX_TILES * 16 * MEGA_TMAX) * 4 + red_max);
+  m = std::max(m, (size_t)(MEGA_TMAX + MEGA_TMAX * MEGA_SQ_STRIDE) * 4 + red_max);
   m = std::max(m, (size_t)(2 * std::max(max_seq, d.cp_max_seq) + 256 + 16 * 2 * 128) * 4 + 2 * 128 * 2);
   return m;
 }

@@ -374,8 +374,8 @@ static MegaArgs mega_args(q3_session* s) {
   const char* e2 = std::getenv("Q3_PREFETCH");
   a.bar_mode = e1 ? std::atoi(e1) : 0;
   a.prefetch_mode = e2 ? std::atoi(e2) : 3;
-  const char* e3 = std::getenv("Q3_DBG");
-  a.dbg = e3 ? std::atoi(e3) : 0;
+  const char* e3 = std::getenv("Q3_SMALL");
+  a.small_mode = e3 ? std::atoi(e3) : 1;
   return a;
 }
 
