@@ -11,6 +11,8 @@
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "mega.cuh"
+#include "mega2.cuh"
+#include "mega3.cuh"
 #include "model.h"
 
 std::atomic<uint64_t> g_q3_launches{0};
@@ -53,6 +55,10 @@ struct q3_session {
   bool prefilled = false, first_sampled = false;
   // persistent frame kernel (batch <= 8)
   bool use_mega = false;
+  int mega_ver = 2;                // 1: fence-based grid barriers (mega.cuh), 2: tagged dataflow phases (mega2.cuh)
+  DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag;
+  int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
+  size_t m2_smem = 0, m3_smem = 0;
   DBuf prof;                       // optional timestamp buffer (q3_debug_profile)
   size_t mega_smem = 0;
   int mega_grid = 0;
@@ -390,6 +396,234 @@ static void mega_launch(q3_session* s, MegaArgs& a) {
   Q3_COUNT_LAUNCH();
 }
 
+
+// ---- persistent frame kernel, dataflow generation (mega2.cuh) ---------------------------------------------
+// The phase program of one frame for the given mode; every pointer is resolved here, once.
+static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_finish, bool do_talker, bool do_sample,
+                                             const bf16* ext_in, float* cp_logits) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  const int B = s->B, G = s->mega_grid, H = d.hidden, C = d.cp_hidden;
+  std::vector<M2Phase> pr;
+  u64* xT = s->m2_x.as<u64>();
+  u64* qkvT = s->m2_qkv.as<u64>();
+  u64* attnT = s->m2_attn.as<u64>();
+  u64* h1T = s->m2_h1.as<u64>();
+  u64* actT = s->m2_act.as<u64>();
+  const char* e_samew = std::getenv("Q3_DEBUG_SAMEW");
+  const bool samew = e_samew && e_samew[0] == '1';
+  auto blank = [](int kind) {
+    M2Phase p;
+    memset(&p, 0, sizeof(p));
+    p.kind = kind; p.xf = XF_NONE; p.rf = XF_NONE; p.yf = XF_NONE;
+    return p;
+  };
+  auto pick_small = [&](M2Phase& p) {
+    const int units = p.N / 8, per_cta = (units + G - 1) / G, tiles = (per_cta + 1) / 2;
+    const bool dual = p.flags & PF_DUAL, norm = p.flags & PF_NORM;
+    p.small = 0;
+    if (dual) {
+      if (norm && p.xf == XF_F32T && p.K == 1024 && tiles <= 2) p.small = 0x21;
+    } else if (norm) {
+      if (p.xf == XF_BF16T && p.K == 1024 && tiles <= 2) p.small = 0x21;
+      else if (p.xf == XF_BF16T && p.K == 2048 && tiles <= 2 && p.T <= 8) p.small = 0x22;
+    } else if (p.xf == XF_GATHER) {
+      if (p.K == 2048 && tiles <= 1) p.small = 0x12;
+    } else if (p.xf == XF_BF16T) {
+      if (p.K == 2048 && tiles <= 1) p.small = 0x12;
+      else if (p.K == 3072 && tiles <= 1) p.small = 0x13;
+    }
+    const char* e = std::getenv("Q3_SMALL");
+    if (e && e[0] == '0') p.small = 0;
+  };
+  auto layers = [&](const std::vector<LayerW>& L, const StackDims& dm, int T, int S, bool cp, int pos_add, bf16* kc, bf16* vc,
+                    int cache_seq) {
+    const int nh = dm.heads + 2 * dm.kv_heads;
+    const size_t layer_stride = (size_t)B * dm.kv_heads * cache_seq * 128;
+    for (int l = 0; l < dm.layers; ++l) {
+      const LayerW& w = samew ? L[0] : L[l];    // Q3_DEBUG_SAMEW=1: timing experiment with L2-resident weights (wrong results)
+      M2Phase q = blank(M2_GEMV);      // rms_norm(x) -> [q;k;v]
+      q.W = w.wqkv; q.N = nh * 128; q.K = dm.H; q.T = T; q.flags = PF_NORM; q.aux = w.in_ln; q.X = xT; q.ldx = dm.H;
+      q.xf = XF_BF16T; q.epi = EPI_STORE; q.Y = qkvT; q.ldy = nh * 128; q.yf = XF_BF16T;
+      pick_small(q); pr.push_back(q);
+      M2Phase at = blank(M2_ATTN);     // QK-norm, RoPE, KV append, attention
+      at.X = qkvT; at.Y = attnT; at.W = kc + l * layer_stride; at.W2 = vc + l * layer_stride; at.aux = w.q_norm;
+      at.aux2 = w.k_norm; at.N = dm.heads; at.K = dm.kv_heads; at.T = T; at.S = S; at.pos_add = pos_add;
+      at.ldx = nh * 128; at.ldy = dm.heads * 128; at.flags = cp ? PF_CP : 0;
+      pr.push_back(at);
+      M2Phase o = blank(M2_GEMV);      // o_proj + residual: h1 = x + attn_out (un-rounded f32 slots)
+      o.W = w.wo; o.N = dm.H; o.K = dm.heads * 128; o.T = T; o.X = attnT; o.ldx = dm.heads * 128; o.xf = XF_BF16T;
+      o.epi = EPI_O_H1; o.R = xT; o.ldr = dm.H; o.rf = XF_BF16T; o.Y = h1T; o.ldy = dm.H; o.yf = XF_F32T;
+      pick_small(o); pr.push_back(o);
+      M2Phase gu = blank(M2_GEMV);     // post-attention RMSNorm -> SwiGLU(gate, up)
+      gu.W = w.gate; gu.W2 = w.up; gu.N = dm.I; gu.K = dm.H; gu.T = T; gu.flags = PF_NORM | PF_DUAL; gu.aux = w.post_ln;
+      gu.X = h1T; gu.ldx = dm.H; gu.xf = XF_F32T; gu.epi = EPI_SWIGLU; gu.Y = actT; gu.ldy = dm.I; gu.yf = XF_BF16T;
+      pick_small(gu); pr.push_back(gu);
+      M2Phase dn = blank(M2_GEMV);     // down_proj + residual -> x
+      dn.W = w.down; dn.N = dm.H; dn.K = dm.I; dn.T = T; dn.X = actT; dn.ldx = dm.I; dn.xf = XF_BF16T;
+      dn.epi = EPI_RESIDUAL; dn.R = h1T; dn.ldr = dm.H; dn.rf = XF_F32T; dn.Y = xT; dn.ldy = dm.H; dn.yf = XF_BF16T;
+      pick_small(dn); pr.push_back(dn);
+    }
+  };
+  {
+    M2Phase p0 = blank(M2_PROLOGUE);
+    p0.flags = PF_WAIT_ACQ | PF_ARRIVE_REL;
+    pr.push_back(p0);
+  }
+  const int n_ac = d.groups - 1;
+  if (do_cp) {
+    for (int g = 0; g < n_ac; ++g) {
+      const int T = g == 0 ? 2 * B : B, S = g == 0 ? 2 : 1;
+      const bf16* emb = g == 0 ? m->codec_emb : m->cp_emb[g - 1];
+      if (m->cp_proj_w) {
+        M2Phase q = blank(M2_GEMV);
+        q.W = m->cp_proj_w; q.N = C; q.K = H; q.T = T; q.xf = XF_GATHER; q.aux2 = emb; q.g = g;
+        q.flags = PF_WAIT_ACQ | (g == 0 ? PF_CP0 : 0); q.aux = m->cp_proj_b; q.epi = EPI_BIAS; q.Y = xT; q.ldy = C;
+        q.yf = XF_BF16T;
+        pick_small(q); pr.push_back(q);
+      } else {
+        M2Phase q = blank(M2_GATHER);
+        q.K = H; q.T = T; q.g = g; q.aux2 = emb; q.Y = xT; q.ldy = C; q.flags = PF_WAIT_ACQ;
+        pr.push_back(q);
+      }
+      layers(m->cl, m->cdims(), T, S, true, g == 0 ? 0 : g + 1, s->cp_k.as<bf16>(), s->cp_v.as<bf16>(), d.cp_max_seq);
+      M2Phase h = blank(M2_GEMV);
+      h.W = m->cp_head[samew ? 0 : g]; h.N = d.cp_vocab; h.K = C; h.T = B; h.flags = PF_NORM | PF_ARRIVE_REL; h.aux = m->cp_norm;
+      h.xf = XF_BF16T;
+      h.X = g == 0 ? (const void*)(reinterpret_cast<const char*>(xT) + (size_t)C * 4) : (const void*)xT;
+      h.ldx = g == 0 ? 2 * C : C;
+      h.epi = EPI_LOGITS; h.amax = s->fs.amax + (size_t)g * B;
+      h.Yf = cp_logits ? cp_logits + (size_t)g * B * d.cp_vocab : nullptr;
+      pick_small(h); pr.push_back(h);
+    }
+  }
+  if (do_finish) {
+    M2Phase f = blank(M2_FINISH);
+    f.Y = xT; f.flags = PF_WAIT_ACQ;
+    pr.push_back(f);
+  }
+  if (do_talker) {
+    if (!do_finish) {
+      M2Phase c = blank(M2_COPYIN);
+      c.X = ext_in; c.Y = xT; c.flags = PF_WAIT_ACQ;
+      pr.push_back(c);
+    }
+    layers(m->tl, m->tdims(), B, 1, false, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq);
+    M2Phase h = blank(M2_GEMV);
+    h.W = m->codec_head; h.N = d.codec_vocab; h.K = H; h.T = B; h.flags = PF_NORM | PF_ARRIVE_REL; h.aux = m->t_norm;
+    h.xf = XF_BF16T; h.X = xT; h.ldx = H; h.xn_out = s->fs.last_hidden; h.epi = EPI_LOGITS; h.Yf = s->logits.as<float>();
+    pick_small(h); pr.push_back(h);
+  }
+  if (do_sample) {
+    M2Phase sp = blank(M2_SAMPLE);
+    sp.flags = PF_WAIT_ACQ | PF_ARRIVE_REL;
+    pr.push_back(sp);
+  }
+  return pr;
+}
+
+static M2Args mega2_args(q3_session* s) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  M2Args a;
+  memset(&a, 0, sizeof(a));
+  a.B = s->B; a.H = d.hidden; a.n_ac = d.groups - 1; a.eps = d.rms_eps;
+  a.fs = s->fs;
+  a.cp_cos = m->cp_cos; a.cp_sin = m->cp_sin; a.t_cos = s->cos_tab.as<bf16>(); a.t_sin = s->sin_tab.as<bf16>();
+  a.max_seq = s->max_seq; a.cp_max_seq = d.cp_max_seq;
+  a.codec_emb = m->codec_emb;
+  for (int i = 0; i < 15; ++i) a.cp_emb[i] = m->cp_emb[i];
+  a.step_input = s->step_input.as<bf16>();
+  SampleArgs sa = make_sample_args(s->cfg, d.codec_vocab, s->B);
+  sa.logits = s->logits.as<float>();
+  sa.seen = s->fs.seen; sa.rng = s->fs.rng; sa.tok_out = s->fs.cur_tok; sa.token_count = s->fs.token_count;
+  sa.done = s->fs.done; sa.offset = s->fs.offset; sa.frame_idx = s->fs.frame_idx; sa.host_flags = nullptr; sa.advance = 1;
+  a.smp = sa;
+  a.bar = s->bar.as<unsigned>();
+  a.tag_ctr = s->m2_tag.as<unsigned>();
+  a.err = s->host_flags_dev + 4;
+  const char* e2 = std::getenv("Q3_PREFETCH");
+  a.prefetch = e2 ? (std::atoi(e2) != 0) : 1;
+  const char* e3 = std::getenv("Q3_PF_SLEEP");
+  a.pf_sleep = e3 ? std::atoi(e3) : 200;
+  const char* e4 = std::getenv("Q3_RING_SHIFT");
+  a.ring_shift = e4 ? std::min(3, std::max(0, std::atoi(e4))) : 3;
+  return a;
+}
+
+static void mega2_check_watchdog(q3_session* s) {
+  if (s->host_flags && s->host_flags[4] != 0) {
+    const int code = s->host_flags[4];
+    s->host_flags[4] = 0;
+    throw Q3Error(Q3_ERR_CUDA, "persistent decode kernel watchdog fired (code " + std::to_string(code) + ")");
+  }
+}
+
+static void mega2_launch(q3_session* s, M2Args& a, const DBuf& prog, int n_ph, bool force_v2 = false) {
+  const unsigned magic = (unsigned)(((1ull << 24) + (unsigned)s->mega_grid - 1) / (unsigned)s->mega_grid);
+  Q3_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_grid_magic, &magic, 4, 0, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemsetAsync(s->bar.p, 0, 4, s->st));
+  a.prog = prog.as<M2Phase>();
+  a.n_ph = n_ph;
+  if (s->prof.p) {
+    a.prof = s->prof.as<unsigned long long>(); a.prof_cap = (int)(s->prof.bytes / 8);
+    const char* pm = std::getenv("Q3_PROF_MODE");
+    a.prof_mode = pm ? std::atoi(pm) : 0;
+    if (a.prof_mode == 2 && (size_t)a.prof_cap < (size_t)(n_ph * 4 + 8) * s->mega_grid + 2048) a.prof_mode = 0;
+  }
+  void* params[] = {(void*)&a};
+  if (s->mega_ver == 3 && !force_v2)
+    Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega3_kernel, dim3(s->mega_grid), dim3(M3_THREADS), params,
+                                              s->m3_smem, s->st));
+  else
+    Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega2_kernel, dim3(s->mega_grid), dim3(MEGA_THREADS), params,
+                                              s->m2_smem, s->st));
+  Q3_COUNT_LAUNCH();
+}
+
+// one-off program (per-op entry points): built, uploaded, launched
+static void mega2_run_mode(q3_session* s, bool do_cp, bool do_finish, bool do_talker, bool do_sample, const bf16* ext_in,
+                           float* cp_logits) {
+  std::vector<M2Phase> pr = m2_build_program(s, do_cp, do_finish, do_talker, do_sample, ext_in, cp_logits);
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));        // the previous one-off program may still be in use
+  s->m2_prog_tmp.ensure(pr.size() * sizeof(M2Phase));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_prog_tmp.p, pr.data(), pr.size() * sizeof(M2Phase), cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));        // pr is a local
+  M2Args a = mega2_args(s);
+  a.n_frames = 1; a.do_sample = do_sample;
+  mega2_launch(s, a, s->m2_prog_tmp, (int)pr.size());
+}
+
+static void run_frames_mega2(q3_session* s, int n) {
+  if (s->m2_n_ph == 0) {
+    std::vector<M2Phase> pr = m2_build_program(s, true, true, true, true, nullptr, nullptr);
+    s->m2_prog.ensure(pr.size() * sizeof(M2Phase));
+    Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_prog.p, pr.data(), pr.size() * sizeof(M2Phase), cudaMemcpyHostToDevice, s->st));
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+    s->m2_n_ph = (int)pr.size();
+  }
+  const int per_launch = 16;
+  int done_frames = 0, blk = 0;
+  bool stop = false;
+  while (done_frames < n && !stop) {
+    const int todo = std::min(per_launch, n - done_frames);
+    M2Args a = mega2_args(s);
+    a.n_frames = todo; a.do_sample = 1;
+    mega2_launch(s, a, s->m2_prog, s->m2_n_ph);
+    done_frames += todo;
+    count_active_kernel<<<1, 32, 0, s->st>>>(s->fs.done, s->B, s->host_flags_dev + (blk & 1));
+    Q3_COUNT_LAUNCH();
+    Q3_CHECK_CUDA(cudaEventRecord(s->ev_poll[blk & 1], s->st));
+    if (blk > 0) {
+      Q3_CHECK_CUDA(cudaEventSynchronize(s->ev_poll[(blk - 1) & 1]));
+      mega2_check_watchdog(s);
+      if (s->host_flags[(blk - 1) & 1] == 0) stop = true;
+    }
+    ++blk;
+  }
+  s->frames_run += done_frames;
+}
+
 static void run_frames_mega(q3_session* s, int n) {
   const int per_launch = 16;
   int done_frames = 0, blk = 0;
@@ -421,7 +655,8 @@ static void run_frames(q3_session* s, int n) {
     throw Q3Error(Q3_ERR_KV_OVERFLOW, "KV cache overflow: current=" + std::to_string(max_len + s->frames_run) +
                                           " + new=" + std::to_string(n) + " > max=" + std::to_string(s->max_seq));
   if (s->use_mega) {
-    run_frames_mega(s, n);
+    if (s->mega_ver >= 2) run_frames_mega2(s, n);
+    else run_frames_mega(s, n);
     return;
   }
   int done_frames = 0;
@@ -782,6 +1017,46 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
         s->ss.zero();
       }
     }
+    s->mega_ver = (env && env[0] == '1') ? 1 : 2;
+    if (s->use_mega && s->mega_ver == 2) {
+      // dataflow generation: tagged activation buffers (8-byte slots), the phase program, the session's tag counter
+      const int n_ph_max = 3 + (d.groups - 1) * (2 + 5 * d.cp_layers) + 1 + 5 * d.layers + 1;
+      s->m2_smem = mega2_smem_bytes(d, B, max_seq, m->num_sms, n_ph_max);
+      int per_sm = 0;
+      if (s->m2_smem > 0 && s->m2_smem <= 227 * 1024) {
+        Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->m2_smem));
+        Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_frames_mega2_kernel, MEGA_THREADS, s->m2_smem));
+      }
+      if (per_sm >= 1) {
+        const size_t Hm = std::max(d.hidden, d.cp_hidden), Im = std::max(d.inter, d.cp_inter);
+        const size_t nhm = (size_t)std::max(d.heads + 2 * d.kv_heads, d.cp_heads + 2 * d.cp_kv_heads) * 128;
+        const size_t qdm = (size_t)std::max(d.heads, d.cp_heads) * 128;
+        s->m2_x.alloc(MEGA_TMAX * Hm * 4); s->m2_qkv.alloc(MEGA_TMAX * nhm * 4); s->m2_attn.alloc(MEGA_TMAX * qdm * 4);
+        s->m2_h1.alloc(MEGA_TMAX * Hm * 8); s->m2_act.alloc(MEGA_TMAX * Im * 4); s->m2_tag.alloc(64);
+        s->m2_x.zero(); s->m2_qkv.zero(); s->m2_attn.zero(); s->m2_h1.zero(); s->m2_act.zero();
+        const unsigned one = 1;
+        Q3_CHECK_CUDA(cudaMemcpy(s->m2_tag.p, &one, 4, cudaMemcpyHostToDevice));
+        s->host_flags[4] = 0;
+        // TMA weight ring (mega3.cuh): every skinny-GEMM phase must be one of its (K, format) combinations
+        const bool want3 = !(env && env[0] == '2');
+        if (want3) {
+          s->mega_grid = m->num_sms;
+          std::vector<M2Phase> pr = m2_build_program(s.get(), true, true, true, true, nullptr, nullptr);
+          bool ok3 = true;
+          for (const M2Phase& ph : pr)
+            if (ph.kind == M2_GEMV && !m3_gemv_supported(ph.K, ph.flags & PF_DUAL, ph.flags & PF_NORM, ph.xf, ph.T)) ok3 = false;
+          s->m3_smem = ok3 ? mega3_smem_bytes(d, B, max_seq, m->num_sms) : 0;
+          int per_sm3 = 0;
+          if (s->m3_smem > 0 && s->m3_smem + 4096 <= 227 * 1024) {
+            Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->m3_smem));
+            Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, decode_frames_mega3_kernel, M3_THREADS, s->m3_smem));
+          }
+          if (per_sm3 >= 1) s->mega_ver = 3;
+        }
+      } else {
+        s->mega_ver = 1;
+      }
+    }
   }
   FrameState& fs = s->fs;
   fs.cur_tok = s->cur_tok.as<uint32_t>(); fs.done = s->done.as<int>(); fs.n_frames = s->n_frames.as<int>();
@@ -816,6 +1091,7 @@ q3_status q3_session_synchronize(q3_session* s) {
   Q3_API_BEGIN
   Q3_REQUIRE(s, Q3_ERR_INVALID, "null session");
   Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  mega2_check_watchdog(s);
   Q3_API_END
 }
 
@@ -972,6 +1248,7 @@ q3_status q3_get_codes(q3_session* s, int32_t max_frames, uint32_t* codes, int32
     Q3_CHECK_CUDA(cudaMemcpy2DAsync(codes, (size_t)max_frames * 64, s->codes.p, (size_t)s->frames_cap * 64, (size_t)take * 64, B,
                                     cudaMemcpyDeviceToHost, s->st));
   Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  mega2_check_watchdog(s);
   for (int b = 0; b < B; ++b) n_frames[b] = std::min(n_frames[b], max_frames);
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) == cudaSuccess) s->timing.generation_ms = ms;
@@ -1109,9 +1386,13 @@ q3_status q3_talker_step(q3_session* s, const uint16_t* step_input, uint16_t* hi
   bf16* x = s->sc.x.as<bf16>();
   if (s->use_mega) {
     Q3_CHECK_CUDA(cudaMemcpyAsync(s->step_input.p, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
-    MegaArgs a = mega_args(s);
-    a.n_frames = 1; a.do_talker = 1; a.ext_step_input = s->step_input.as<bf16>();
-    mega_launch(s, a);
+    if (s->mega_ver >= 2) {
+      mega2_run_mode(s, false, false, true, false, s->step_input.as<bf16>(), nullptr);
+    } else {
+      MegaArgs a = mega_args(s);
+      a.n_frames = 1; a.do_talker = 1; a.ext_step_input = s->step_input.as<bf16>();
+      mega_launch(s, a);
+    }
   } else {
     Q3_CHECK_CUDA(cudaMemcpyAsync(x, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
     layers_forward(s, s->m->tl, s->m->tdims(), x, s->B, 1, s->fs.offset, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq,
@@ -1124,6 +1405,7 @@ q3_status q3_talker_step(q3_session* s, const uint16_t* step_input, uint16_t* hi
   if (hidden_out) Q3_CHECK_CUDA(cudaMemcpyAsync(hidden_out, s->last_hidden.p, (size_t)s->B * d.hidden * 2, cudaMemcpyDeviceToHost, s->st));
   if (logits_out) Q3_CHECK_CUDA(cudaMemcpyAsync(logits_out, s->logits.p, (size_t)s->B * d.codec_vocab * 4, cudaMemcpyDeviceToHost, s->st));
   Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  mega2_check_watchdog(s);
   Q3_API_END
 }
 
@@ -1140,9 +1422,13 @@ q3_status q3_code_predictor_frame(q3_session* s, const uint16_t* last_hidden, co
   if (logits_out) s->cp_logits.ensure((size_t)n_ac * B * d.cp_vocab * 4);
   if (s->use_mega) {
     ensure_scratch(s, 2 * B);
-    MegaArgs a = mega_args(s);
-    a.n_frames = 1; a.do_cp = 1; a.cp_logits = logits_out ? s->cp_logits.as<float>() : nullptr;
-    mega_launch(s, a);
+    if (s->mega_ver >= 2) {
+      mega2_run_mode(s, true, false, false, false, nullptr, logits_out ? s->cp_logits.as<float>() : nullptr);
+    } else {
+      MegaArgs a = mega_args(s);
+      a.n_frames = 1; a.do_cp = 1; a.cp_logits = logits_out ? s->cp_logits.as<float>() : nullptr;
+      mega_launch(s, a);
+    }
   } else {
     cp_frame(s, logits_out ? s->cp_logits.as<float>() : nullptr);
   }
@@ -1230,10 +1516,16 @@ q3_status q3_debug_profile(q3_session* s, int32_t frames, uint64_t* stamps, int3
   s->prof.zero(s->st);
   unsigned zero = 0;
   Q3_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_prof_idx, &zero, 4, 0, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_prof2_idx, &zero, 4, 0, cudaMemcpyHostToDevice, s->st));
   run_frames(s, frames);
   Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
   unsigned n = 0;
-  Q3_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_prof_idx, 4));
+  if (s->mega_ver >= 2) Q3_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_prof2_idx, 4));
+  else Q3_CHECK_CUDA(cudaMemcpyFromSymbol(&n, g_prof_idx, 4));
+  {
+    const char* pm = std::getenv("Q3_PROF_MODE");
+    if (pm && std::atoi(pm) == 2) n = (unsigned)cap;
+  }
   *n_out = (int)std::min<unsigned>(n, (unsigned)cap);
   Q3_CHECK_CUDA(cudaMemcpy(stamps, s->prof.p, (size_t)(*n_out) * 8, cudaMemcpyDeviceToHost));
   s->prof.release();
@@ -1245,6 +1537,21 @@ q3_status q3_debug_barrier_bench(q3_session* s, int32_t n, float* ms_out) {
   Q3_API_BEGIN
   Q3_REQUIRE(s && ms_out && s->use_mega, Q3_ERR_STATE, "needs the persistent path");
   Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  if (s->mega_ver >= 2) {
+    // odd n: release/acquire barriers, even n: relaxed (hint) barriers
+    std::vector<M2Phase> pr = m2_build_program(s, false, false, false, false, nullptr, nullptr);
+    s->m2_prog_tmp.ensure(pr.size() * sizeof(M2Phase));
+    Q3_CHECK_CUDA(cudaMemcpy(s->m2_prog_tmp.p, pr.data(), pr.size() * sizeof(M2Phase), cudaMemcpyHostToDevice));
+    M2Args a = mega2_args(s);
+    a.bench_barriers = n;
+    mega2_launch(s, a, s->m2_prog_tmp, (int)pr.size(), true);
+    Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
+    mega2_launch(s, a, s->m2_prog_tmp, (int)pr.size(), true);
+    Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+    Q3_CHECK_CUDA(cudaEventElapsedTime(ms_out, s->ev0, s->ev1));
+    return Q3_OK;
+  }
   MegaArgs a = mega_args(s);
   a.bench_barriers = n;
   mega_launch(s, a);
