@@ -56,6 +56,8 @@ struct q3_session {
   // persistent frame kernel (batch <= 8)
   bool use_mega = false;
   int mega_ver = 2;                // 1: fence-based grid barriers (mega.cuh), 2: tagged dataflow phases (mega2.cuh)
+  DBuf tr_ids, tr_proj;            // staging of q3_set_trailing_ids
+  DBuf pf_tid, pf_cid;             // staging of q3_prefill_ids
   DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag;
   int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
   size_t m2_smem = 0, m3_smem = 0;
@@ -1038,7 +1040,7 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
         Q3_CHECK_CUDA(cudaMemcpy(s->m2_tag.p, &one, 4, cudaMemcpyHostToDevice));
         s->host_flags[4] = 0;
         // TMA weight ring (mega3.cuh): every skinny-GEMM phase must be one of its (K, format) combinations
-        const bool want3 = !(env && env[0] == '2');
+        const bool want3 = env && env[0] == '3';     // experimental: slower than the dataflow kernel on B200
         if (want3) {
           s->mega_grid = m->num_sms;
           std::vector<M2Phase> pr = m2_build_program(s.get(), true, true, true, true, nullptr, nullptr);
@@ -1149,8 +1151,9 @@ q3_status q3_prefill_ids(q3_session* s, const int32_t* text_ids, const int32_t* 
     Q3_REQUIRE(text_ids[i] < d.text_vocab && codec_ids[i] < d.codec_vocab, Q3_ERR_INVALID, "token id out of range");
   }
   ensure_scratch(s, T);
-  DBuf tid, cid;
-  tid.alloc(T * 4); cid.alloc(T * 4);
+  DBuf& tid = s->pf_tid;
+  DBuf& cid = s->pf_cid;
+  tid.ensure((size_t)T * 4); cid.ensure((size_t)T * 4);
   Q3_CHECK_CUDA(cudaMemcpyAsync(tid.p, text_ids, T * 4, cudaMemcpyHostToDevice, s->st));
   Q3_CHECK_CUDA(cudaMemcpyAsync(cid.p, codec_ids, T * 4, cudaMemcpyHostToDevice, s->st));
   text_project(s, tid.as<int>(), T, s->sc.o.as<bf16>());
@@ -1204,9 +1207,11 @@ q3_status q3_set_trailing_ids(q3_session* s, const int32_t* ids, const int32_t* 
     lt[b] = n[b] + 1;
   }
   const int T = B * lt_max + 1;
-  DBuf idd, proj;
-  idd.alloc(T * 4);
-  proj.alloc((size_t)T * H * 2);
+  // session-owned staging buffers: a cudaMalloc/cudaFree pair per call cost 70-450 ms once the vocoder workspace existed
+  DBuf& idd = s->tr_ids;
+  DBuf& proj = s->tr_proj;
+  idd.ensure((size_t)T * 4);
+  proj.ensure((size_t)T * H * 2);
   Q3_CHECK_CUDA(cudaMemcpyAsync(idd.p, all.data(), T * 4, cudaMemcpyHostToDevice, s->st));
   text_project(s, idd.as<int>(), T, proj.as<bf16>());
   s->trailing.ensure((size_t)B * lt_max * H * 2);
