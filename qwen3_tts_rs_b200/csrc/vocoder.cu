@@ -103,6 +103,8 @@ void launch_mma(MmaConvArgs& a, int grid_q, int Cout_pad, int z, cudaStream_t st
     configured = true;
   }
   Q3_REQUIRE(smem <= 100 * 1024, Q3_ERR_UNSUPPORTED, "conv window too large for the staged tile");
+  Q3_REQUIRE((MC_BK / 2) * (MC_BN + a.max_shift - a.min_shift) <= 12 * 256, Q3_ERR_UNSUPPORTED,
+             "conv window too large for the register-prefetched staging");
   voc_conv_mma_kernel<<<dim3(grid_q, Cout_pad / MC_BM, z), 256, smem, st>>>(a);
   Q3_COUNT_LAUNCH();
   Q3_LAUNCH_CHECK();

@@ -99,31 +99,54 @@ __global__ void __launch_bounds__(256, 2) voc_conv_mma_kernel(const MmaConvArgs 
 
   const int total_steps = chunks * a.ntaps;
   load_A(0, 0, 0);
-  for (int chunk = 0; chunk < chunks; ++chunk) {
-    // ---- stage the activation window of this channel chunk: positions q0+min_shift .. q0+127+max_shift ----
-    __syncthreads();                                         // previous chunk's readers are done with Bs
+  // A thread's (up to 12) loads of the activation window are issued back to back before any of them is used: ncu on
+  // the late decoder blocks showed 32% (k=7 convs) to 64% (1x1 convs) of the warp stalls on these loads when each
+  // one was consumed right after it was issued (a chain of ~11 exposed global-memory latencies per channel chunk).
+  // Keeping them in flight ACROSS the tap loop instead spills (64 accumulators + fragments + 24 values > 128 regs).
+  constexpr int MC_NP = 12;                                 // >= 16 channel pairs * (128 + 54 halo) rows / 256 threads
+  const int n_pairs = (MC_BK / 2) * brows;
+  float pv0[MC_NP], pv1[MC_NP];
+  auto fetch_window = [&](int chunk) {
     const int c0 = chunk * MC_BK;
-    for (int i = tid; i < (MC_BK / 2) * brows; i += 256) {
-      const int cp = i / brows, r = i - cp * brows;          // channel pair, window row (consecutive threads: consecutive t)
-      const int t = q0 + a.min_shift + r;
-      float v0 = 0.f, v1 = 0.f;
-      const int ci = c0 + 2 * cp;
-      if (t >= 0 && t < a.Tin) {
-        if (ci < a.Cin) {
-          v0 = xb[(size_t)ci * a.Tin + t];
-          if (a.snake_a) v0 = snake_f(v0, a.snake_a[ci], a.snake_ib[ci]);
-        }
-        if (ci + 1 < a.Cin) {
-          v1 = xb[(size_t)(ci + 1) * a.Tin + t];
-          if (a.snake_a) v1 = snake_f(v1, a.snake_a[ci + 1], a.snake_ib[ci + 1]);
+#pragma unroll
+    for (int j = 0; j < MC_NP; ++j) {
+      const int i = tid + j * 256;
+      pv0[j] = 0.f; pv1[j] = 0.f;
+      if (i < n_pairs) {
+        const int cp = i / brows, r = i - cp * brows;       // channel pair, window row (consecutive threads: consecutive t)
+        const int t = q0 + a.min_shift + r;
+        const int ci = c0 + 2 * cp;
+        if (t >= 0 && t < a.Tin) {
+          if (ci < a.Cin) pv0[j] = __ldg(xb + (size_t)ci * a.Tin + t);
+          if (ci + 1 < a.Cin) pv1[j] = __ldg(xb + (size_t)(ci + 1) * a.Tin + t);
         }
       }
-      const bf16 h0 = f2bf(v0), h1 = f2bf(v1);
-      const bf16 l0 = f2bf(v0 - bf2f(h0)), l1 = f2bf(v1 - bf2f(h1));
-      __nv_bfloat162 hh, ll;
-      hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
-      *reinterpret_cast<__nv_bfloat162*>(Bs_hi + (size_t)r * MC_PITCH + 2 * cp) = hh;
-      *reinterpret_cast<__nv_bfloat162*>(Bs_lo + (size_t)r * MC_PITCH + 2 * cp) = ll;
+    }
+  };
+  for (int chunk = 0; chunk < chunks; ++chunk) {
+    // ---- stage the activation window of this channel chunk: positions q0+min_shift .. q0+127+max_shift ----
+    fetch_window(chunk);                                     // all of this thread's loads in flight together
+    __syncthreads();                                         // previous chunk's readers are done with Bs
+    const int c0 = chunk * MC_BK;
+#pragma unroll
+    for (int j = 0; j < MC_NP; ++j) {
+      const int i = tid + j * 256;
+      if (i < n_pairs) {
+        const int cp = i / brows, r = i - cp * brows;
+        const int t = q0 + a.min_shift + r;
+        const int ci = c0 + 2 * cp;
+        float v0 = pv0[j], v1 = pv1[j];
+        if (a.snake_a && t >= 0 && t < a.Tin) {             // out-of-range positions are zero padding, not snake(0)
+          if (ci < a.Cin) v0 = snake_f(v0, a.snake_a[ci], a.snake_ib[ci]);
+          if (ci + 1 < a.Cin) v1 = snake_f(v1, a.snake_a[ci + 1], a.snake_ib[ci + 1]);
+        }
+        const bf16 h0 = f2bf(v0), h1 = f2bf(v1);
+        const bf16 l0 = f2bf(v0 - bf2f(h0)), l1 = f2bf(v1 - bf2f(h1));
+        __nv_bfloat162 hh, ll;
+        hh.x = h0; hh.y = h1; ll.x = l0; ll.y = l1;
+        *reinterpret_cast<__nv_bfloat162*>(Bs_hi + (size_t)r * MC_PITCH + 2 * cp) = hh;
+        *reinterpret_cast<__nv_bfloat162*>(Bs_lo + (size_t)r * MC_PITCH + 2 * cp) = ll;
+      }
     }
     for (int tap = 0; tap < a.ntaps; ++tap) {
       const int step = chunk * a.ntaps + tap;
