@@ -86,6 +86,11 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# one `ncu --set full` capture of decode_frames_mega2_kernel at the bench shape (1.7B, batch 8): 73.39 GB read +
+# 0.50 GB written per 16-frame launch
+NCU_TRAFFIC_PER_FRAME = (73.394839e9 + 0.497831e9) / 16.0
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -301,10 +306,13 @@ def main():
                                       "ms_per_frame": loop_ms_max / max(1, frames_run),
                                       "vocoder": dec_ms / args.steps, "prefill": prefill_ms,
                                       "vocoder_tflops_f32_equiv": (total_frames_step / world) * 4.959e9 / (dec_ms / args.steps / 1e3) / 1e12},
-            "roofline": {"kernel": "decode_frames_mega_kernel, per frame (one persistent cooperative launch runs 16 frames: 15 code-predictor "
+            "roofline": {"kernel": "decode_frames_mega2_kernel, per frame (one persistent cooperative launch runs 16 frames: 15 code-predictor "
                                    "passes + 28-layer talker step + codec head + sampler for all rows)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src, "traffic": None,
+                         "peak_source": peak_src,
+                         # dram__bytes_read + dram__bytes_write of one 16-frame launch / 16 (profiles/r1_mega2_full.summary.txt);
+                         # below the algorithmic bytes because part of the code-predictor weights stay in L2 between passes
+                         "traffic": NCU_TRAFFIC_PER_FRAME if (spec.name == "1.7b" and B == 8) else None,
                          "algorithmic_bytes_per_launch": bytes_step, "launch_ms": t_frame * 1e3},
             "e2e": {"value": e2e_value, "unit": "frames/s",
                     "rtf": (e2e_ms_max / 1e3) / (total_frames_step * args.steps * 0.08),
