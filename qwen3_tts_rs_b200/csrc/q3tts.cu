@@ -545,7 +545,7 @@ static M2Args mega2_args(q3_session* s) {
   a.tag_ctr = s->m2_tag.as<unsigned>();
   a.err = s->host_flags_dev + 4;
   const char* e2 = std::getenv("Q3_PREFETCH");
-  a.prefetch = e2 ? (std::atoi(e2) != 0) : 1;
+  a.prefetch = e2 ? std::atoi(e2) : 2;      // 0: none, 1: next phase's rows at phase end, 2: + gate/up rows at attention start
   const char* e3 = std::getenv("Q3_PF_SLEEP");
   a.pf_sleep = e3 ? std::atoi(e3) : 200;
   const char* e4 = std::getenv("Q3_RING_SHIFT");
