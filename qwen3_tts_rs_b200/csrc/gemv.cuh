@@ -223,14 +223,20 @@ template <int TB, int RPW, bool DUAL>
 static void gemv_launch_inst(const GemvArgs& a, int grid, cudaStream_t st) {
   size_t smem = (size_t)TB * a.K * sizeof(bf16);
   static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  if (smem > 32 * 1024 && smem > configured) {       // static shared memory counts against the 48 KB default too
     Q3_CHECK_CUDA(cudaFuncSetAttribute(gemv_kernel<TB, RPW, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(200 * 1024)));
     configured = 200 * 1024;
   }
   gemv_kernel<TB, RPW, DUAL><<<grid, 256, smem, st>>>(a);
   Q3_COUNT_LAUNCH();
-  Q3_LAUNCH_CHECK();
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+      throw Q3Error(Q3_ERR_CUDA, std::string("gemv launch failed: ") + cudaGetErrorString(e) + " (TB " + std::to_string(TB) + ", RPW " +
+                                     std::to_string(RPW) + ", N " + std::to_string(a.N) + ", K " + std::to_string(a.K) + ", T " +
+                                     std::to_string(a.T) + ", grid " + std::to_string(grid) + ", smem " + std::to_string(smem) + ")");
+  }
 }
 
 template <int TB, bool DUAL>
