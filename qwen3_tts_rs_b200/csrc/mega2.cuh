@@ -247,7 +247,7 @@ __device__ __forceinline__ void m2_token_rows(const M2Args& a, const M2Phase& p,
     if (t < T) {
       if constexpr (XF == XF_GATHER) {
         if (p.flags & PF_CP0) {
-          const int b = t >> 1;
+          const int b = (t >> 1) + p.pos_add;          // pos_add: first batch row of this pass-0 group (batch > 8)
           xrow[nt] = reinterpret_cast<const char*>((t & 1) ? p.aux2 + (size_t)__ldcg(a.fs.cur_tok + b) * K
                                                            : a.fs.last_hidden + (size_t)b * K);
         } else {
@@ -264,7 +264,7 @@ __device__ __forceinline__ void m2_token_rows(const M2Args& a, const M2Phase& p,
       const int tid = threadIdx.x;
       if (!(p.flags & PF_CP0) && tid < T)
         a.fs.frame_codes[tid * 16 + p.g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(p.g - 1) * a.B + tid));
-      if ((p.flags & PF_CP0) && tid < a.B) a.fs.frame_codes[tid * 16] = __ldcg(a.fs.cur_tok + tid);
+      if ((p.flags & PF_CP0) && tid < (T >> 1)) a.fs.frame_codes[(tid + p.pos_add) * 16] = __ldcg(a.fs.cur_tok + tid + p.pos_add);
     }
   }
 }
@@ -880,7 +880,7 @@ __device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t xtag = tag - 1u;
   const float scale = rbf(0.08838834764831845f);
-  const int n_items = a.B * kv_heads;
+  const int n_items = (p.T / p.S) * kv_heads;       // rows of this phase (a pass-0 group of a batch > 8 has fewer than a.B)
   const bool worker = (int)blockIdx.x < n_items;
   // rows that can be requested before the wait (fast path, first token of the item)
   int b0 = 0, pos0 = 0;
@@ -1213,14 +1213,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega2_kernel(co
               const int t = k / K8, qq = k - t * K8;
               const bf16* src;
               if (g == 0) {
-                const int b = t >> 1;
+                const int b = (t >> 1) + p.pos_add;
                 src = (t & 1) ? p.aux2 + (size_t)__ldcg(a.fs.cur_tok + b) * p.K : a.fs.last_hidden + (size_t)b * p.K;
               } else {
                 src = p.aux2 + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + t)) * p.K;
               }
               m2_store_row8(reinterpret_cast<u64*>(p.Y) + (((size_t)t * p.ldy + qq * 8) >> 1), ldcg16(src + qq * 8), tag);
             }
-            if (g == 0) { if (threadIdx.x < B) a.fs.frame_codes[threadIdx.x * 16] = __ldcg(a.fs.cur_tok + threadIdx.x); }
+            if (g == 0) { if ((int)threadIdx.x < (T >> 1)) a.fs.frame_codes[(threadIdx.x + p.pos_add) * 16] = __ldcg(a.fs.cur_tok + threadIdx.x + p.pos_add); }
             else if (threadIdx.x < B)
               a.fs.frame_codes[threadIdx.x * 16 + g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + threadIdx.x));
           }
@@ -1267,8 +1267,11 @@ static size_t mega2_smem_bytes(const q3_model_desc& d, int B, int max_seq, int g
     red_max = std::max(red_max, (size_t)NT * (dual ? 2 : 1) * 8 * (256 * tiles + 4) * 4);
   };
   const int nh = (d.heads + 2 * d.kv_heads) * 128, cnh = (d.cp_heads + 2 * d.cp_kv_heads) * 128;
+  // code-predictor pass 0 has two tokens per row: batches above 8 run it in row groups of 8 (m2_build_program)
+  const int T0 = 2 * std::min(B, 8), T1 = B;
   phase(nh, B, false); phase(d.hidden, B, false); phase(d.inter, B, true); phase(d.codec_vocab, B, false);
-  phase(d.cp_hidden, 2 * B, false); phase(cnh, 2 * B, false); phase(d.cp_inter, 2 * B, true); phase(d.cp_vocab, B, false);
+  phase(d.cp_hidden, std::max(T0, T1), false); phase(cnh, std::max(T0, T1), false); phase(d.cp_inter, std::max(T0, T1), true);
+  phase(d.cp_vocab, B, false);
   if (!ok || n_ph > M2_MAX_PHASES) return 0;
   size_t m = sizeof(SampleSmem);
   m = std::max(m, (size_t)M2_RED_OFF + red_max);

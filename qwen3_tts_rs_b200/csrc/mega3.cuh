@@ -415,14 +415,14 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_frames_mega3_kernel(cons
                 const int t = k / K8, qq = k - t * K8;
                 const bf16* src;
                 if (g == 0) {
-                  const int b = t >> 1;
+                  const int b = (t >> 1) + p.pos_add;
                   src = (t & 1) ? p.aux2 + (size_t)__ldcg(a.fs.cur_tok + b) * p.K : a.fs.last_hidden + (size_t)b * p.K;
                 } else {
                   src = p.aux2 + (size_t)argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + t)) * p.K;
                 }
                 m2_store_row8(reinterpret_cast<u64*>(p.Y) + (((size_t)t * p.ldy + qq * 8) >> 1), ldcg16(src + qq * 8), tag);
               }
-              if (g == 0) { if (threadIdx.x < B) a.fs.frame_codes[threadIdx.x * 16] = __ldcg(a.fs.cur_tok + threadIdx.x); }
+              if (g == 0) { if ((int)threadIdx.x < (T >> 1)) a.fs.frame_codes[(threadIdx.x + p.pos_add) * 16] = __ldcg(a.fs.cur_tok + threadIdx.x + p.pos_add); }
               else if (threadIdx.x < B)
                 a.fs.frame_codes[threadIdx.x * 16 + g] = argmax_key_index(__ldcg(a.fs.amax + (size_t)(g - 1) * B + threadIdx.x));
             }

@@ -439,9 +439,10 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
     if (e && e[0] == '0') p.small = 0;
   };
   auto layers = [&](const std::vector<LayerW>& L, const StackDims& dm, int T, int S, bool cp, int pos_add, bf16* kc, bf16* vc,
-                    int cache_seq) {
+                    int cache_seq, int row0) {
     const int nh = dm.heads + 2 * dm.kv_heads;
     const size_t layer_stride = (size_t)B * dm.kv_heads * cache_seq * 128;
+    const size_t row_off = (size_t)row0 * dm.kv_heads * cache_seq * 128;     // first batch row of this group in the caches
     for (int l = 0; l < dm.layers; ++l) {
       const LayerW& w = samew ? L[0] : L[l];    // Q3_DEBUG_SAMEW=1: timing experiment with L2-resident weights (wrong results)
       M2Phase q = blank(M2_GEMV);      // rms_norm(x) -> [q;k;v]
@@ -449,7 +450,7 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
       q.xf = XF_BF16T; q.epi = EPI_STORE; q.Y = qkvT; q.ldy = nh * 128; q.yf = XF_BF16T;
       pick_small(q); pr.push_back(q);
       M2Phase at = blank(M2_ATTN);     // QK-norm, RoPE, KV append, attention
-      at.X = qkvT; at.Y = attnT; at.W = kc + l * layer_stride; at.W2 = vc + l * layer_stride; at.aux = w.q_norm;
+      at.X = qkvT; at.Y = attnT; at.W = kc + l * layer_stride + row_off; at.W2 = vc + l * layer_stride + row_off; at.aux = w.q_norm;
       at.aux2 = w.k_norm; at.N = dm.heads; at.K = dm.kv_heads; at.T = T; at.S = S; at.pos_add = pos_add;
       at.ldx = nh * 128; at.ldy = dm.heads * 128; at.flags = cp ? PF_CP : 0;
       pr.push_back(at);
@@ -475,28 +476,34 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
   const int n_ac = d.groups - 1;
   if (do_cp) {
     for (int g = 0; g < n_ac; ++g) {
-      const int T = g == 0 ? 2 * B : B, S = g == 0 ? 2 : 1;
-      const bf16* emb = g == 0 ? m->codec_emb : m->cp_emb[g - 1];
-      if (m->cp_proj_w) {
-        M2Phase q = blank(M2_GEMV);
-        q.W = m->cp_proj_w; q.N = C; q.K = H; q.T = T; q.xf = XF_GATHER; q.aux2 = emb; q.g = g;
-        q.flags = PF_WAIT_ACQ | (g == 0 ? PF_CP0 : 0); q.aux = m->cp_proj_b; q.epi = EPI_BIAS; q.Y = xT; q.ldy = C;
-        q.yf = XF_BF16T;
-        pick_small(q); pr.push_back(q);
-      } else {
-        M2Phase q = blank(M2_GATHER);
-        q.K = H; q.T = T; q.g = g; q.aux2 = emb; q.Y = xT; q.ldy = C; q.flags = PF_WAIT_ACQ;
-        pr.push_back(q);
+      // pass 0 carries two tokens per row (last hidden, semantic embedding): batches above 8 run it in row groups of 8
+      // so that no phase exceeds MEGA_TMAX = 16 tokens; the later passes have one token per row.
+      const int group = g == 0 ? std::min(B, MEGA_TMAX / 2) : B;
+      for (int row0 = 0; row0 < B; row0 += group) {
+        const int Bg = std::min(group, B - row0);
+        const int T = g == 0 ? 2 * Bg : Bg, S = g == 0 ? 2 : 1;
+        const bf16* emb = g == 0 ? m->codec_emb : m->cp_emb[g - 1];
+        if (m->cp_proj_w) {
+          M2Phase q = blank(M2_GEMV);
+          q.W = m->cp_proj_w; q.N = C; q.K = H; q.T = T; q.xf = XF_GATHER; q.aux2 = emb; q.g = g; q.pos_add = row0;
+          q.flags = PF_WAIT_ACQ | (g == 0 ? PF_CP0 : 0); q.aux = m->cp_proj_b; q.epi = EPI_BIAS; q.Y = xT; q.ldy = C;
+          q.yf = XF_BF16T;
+          pick_small(q); pr.push_back(q);
+        } else {
+          M2Phase q = blank(M2_GATHER);
+          q.K = H; q.T = T; q.g = g; q.aux2 = emb; q.Y = xT; q.ldy = C; q.flags = PF_WAIT_ACQ; q.pos_add = row0;
+          pr.push_back(q);
+        }
+        layers(m->cl, m->cdims(), T, S, true, g == 0 ? 0 : g + 1, s->cp_k.as<bf16>(), s->cp_v.as<bf16>(), d.cp_max_seq, row0);
+        M2Phase h = blank(M2_GEMV);
+        h.W = m->cp_head[samew ? 0 : g]; h.N = d.cp_vocab; h.K = C; h.T = Bg; h.flags = PF_NORM | PF_ARRIVE_REL; h.aux = m->cp_norm;
+        h.xf = XF_BF16T;
+        h.X = g == 0 ? (const void*)(reinterpret_cast<const char*>(xT) + (size_t)C * 4) : (const void*)xT;
+        h.ldx = g == 0 ? 2 * C : C;
+        h.epi = EPI_LOGITS; h.amax = s->fs.amax + (size_t)g * B + row0;
+        h.Yf = cp_logits ? cp_logits + ((size_t)g * B + row0) * d.cp_vocab : nullptr;
+        pick_small(h); pr.push_back(h);
       }
-      layers(m->cl, m->cdims(), T, S, true, g == 0 ? 0 : g + 1, s->cp_k.as<bf16>(), s->cp_v.as<bf16>(), d.cp_max_seq);
-      M2Phase h = blank(M2_GEMV);
-      h.W = m->cp_head[samew ? 0 : g]; h.N = d.cp_vocab; h.K = C; h.T = B; h.flags = PF_NORM | PF_ARRIVE_REL; h.aux = m->cp_norm;
-      h.xf = XF_BF16T;
-      h.X = g == 0 ? (const void*)(reinterpret_cast<const char*>(xT) + (size_t)C * 4) : (const void*)xT;
-      h.ldx = g == 0 ? 2 * C : C;
-      h.epi = EPI_LOGITS; h.amax = s->fs.amax + (size_t)g * B;
-      h.Yf = cp_logits ? cp_logits + (size_t)g * B * d.cp_vocab : nullptr;
-      pick_small(h); pr.push_back(h);
     }
   }
   if (do_finish) {
@@ -510,7 +517,7 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
       c.X = ext_in; c.Y = xT; c.flags = PF_WAIT_ACQ;
       pr.push_back(c);
     }
-    layers(m->tl, m->tdims(), B, 1, false, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq);
+    layers(m->tl, m->tdims(), B, 1, false, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq, 0);
     M2Phase h = blank(M2_GEMV);
     h.W = m->codec_head; h.N = d.codec_vocab; h.K = H; h.T = B; h.flags = PF_NORM | PF_ARRIVE_REL; h.aux = m->t_norm;
     h.xf = XF_BF16T; h.X = xT; h.ldx = H; h.xn_out = s->fs.last_hidden; h.epi = EPI_LOGITS; h.Yf = s->logits.as<float>();
@@ -1020,9 +1027,17 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
       }
     }
     s->mega_ver = (env && env[0] == '1') ? 1 : 2;
+    const bool v1_ok = s->use_mega;
+    const bool dims_ok = d.layers + d.cp_layers <= MEGA_MAX_LAYERS && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 && d.inter % 32 == 0 &&
+                         d.cp_inter % 32 == 0 && d.codec_vocab % 16 == 0 && d.cp_vocab % 16 == 0;
+    // the dataflow generation also takes batches 9..16 (code-predictor pass 0 in two row groups)
+    if (want && s->mega_ver == 2 && dims_ok && B <= MEGA_TMAX) {
+      s->use_mega = true;
+      s->mega_grid = m->num_sms;
+    }
     if (s->use_mega && s->mega_ver == 2) {
       // dataflow generation: tagged activation buffers (8-byte slots), the phase program, the session's tag counter
-      const int n_ph_max = 3 + (d.groups - 1) * (2 + 5 * d.cp_layers) + 1 + 5 * d.layers + 1;
+      const int n_ph_max = 3 + (d.groups - 1 + (B > 8 ? 1 : 0)) * (2 + 5 * d.cp_layers) + 1 + 5 * d.layers + 1;
       s->m2_smem = mega2_smem_bytes(d, B, max_seq, m->num_sms, n_ph_max);
       int per_sm = 0;
       if (s->m2_smem > 0 && s->m2_smem <= 227 * 1024) {
@@ -1055,8 +1070,10 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
           }
           if (per_sm3 >= 1) s->mega_ver = 3;
         }
-      } else {
+      } else if (v1_ok) {
         s->mega_ver = 1;
+      } else {
+        s->use_mega = false;
       }
     }
   }

@@ -199,18 +199,18 @@ def test_missing_weight_is_an_error():
 
 
 def test_multi_kernel_path_rows_independent_and_matches_oracle_tolerance(monkeypatch):
-    """The multi-kernel (CUDA-graph) decode path -- used for batch > 8 per GPU -- is kept honest: a batch of 12
+    """The multi-kernel (CUDA-graph) decode path -- used for batch > 16 per GPU -- is kept honest: a batch of 20
     (forced onto it by size) is bit-identical, row by row, to batch-1 runs forced onto the same path with Q3_MEGA=0,
     and its forks from the oracle happen only at near-ties."""
     spec = S.SPEC_TINY_PROJ
-    B, F = 12, 10
+    B, F = 20, 10
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(i, spec) for i in range(B)]
     seeds = [7 + i for i in range(B)]
     tts = gpu_tts(spec)
     big = tts.generate_codes(prompts, options=opts, seeds=seeds)
     monkeypatch.setenv("Q3_MEGA", "0")
-    for i in (0, 5, 11):
+    for i in (0, 5, 19):
         single = tts.generate_codes([prompts[i]], options=opts, seeds=[seeds[i]])[0]
         assert single == big[i], i
     ref, tr, _ = oracle_run(spec, prompts[2], seeds[2], opts, trace=True)
@@ -260,3 +260,20 @@ def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
     assert ok, (mega, m, why)
     single = tts.generate_codes([prompts[2]], options=opts, seeds=[seeds[2]])[0]
     assert single == a[2]
+
+
+def test_batch_16_runs_on_the_persistent_kernel_and_rows_stay_independent():
+    """Batches 9..16 stay on the dataflow kernel (code-predictor pass 0 in two row groups of 8): rows of a batch-16
+    and of a batch-11 run are bit-identical to batch-1 runs with the same prompt and seed, and a second run repeats."""
+    spec = S.SPEC_MID
+    F = 20
+    opts = api.SynthesisOptions(max_length=F)
+    tts = gpu_tts(spec)
+    for B in (16, 11):
+        prompts = [W.synthetic_prompt(30 + i, spec) for i in range(B)]
+        seeds = [500 + i for i in range(B)]
+        a = tts.generate_codes(prompts, options=opts, seeds=seeds)
+        assert a == tts.generate_codes(prompts, options=opts, seeds=seeds)
+        for i in (0, 7, 8, B - 1):
+            single = tts.generate_codes([prompts[i]], options=opts, seeds=[seeds[i]])[0]
+            assert single == a[i], (B, i)
