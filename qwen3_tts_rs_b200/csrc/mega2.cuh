@@ -510,17 +510,31 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) sq[nt] = 0.f;
     if constexpr (XRES) {
+      // both chunks' slots in one batch of loads (one round trip instead of two)
+      unsigned tries = 0;
+      for (;;) {
+        uint32_t bad = 0;
+        float sqa[XC][NT];
 #pragma unroll
-      for (int c = 0; c < XC; ++c) {
-        if (c < n_chunks) {
-          load_x_sync(c);
+        for (int c = 0; c < XC; ++c)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) {
-            sq[nt] += sqc[nt];
+            sqa[c][nt] = 0.f;
 #pragma unroll
-            for (int u = 0; u < JU; ++u) xres[c][u][nt] = xv[nt][u];
+            for (int u = 0; u < JU; ++u) {
+              xres[c][u][nt] = make_uint4(0, 0, 0, 0);
+              if (c < n_chunks && xrow[nt] != nullptr)
+                xres[c][u][nt] = m2_load_x8<XF>(xrow[nt], koff0 + (c * JU + u) * 512, xtag, bad, sqa[c][nt]);
+            }
           }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          sq[nt] = sqa[0][nt];
+          if (XC > 1) sq[nt] += sqa[XC - 1][nt];
         }
+        if (!__any_sync(0xffffffffu, bad != 0)) break;
+        if (gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+        if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 3500000 + (int)gs.epoch); break; }
       }
     } else {
       for (int c = 0; c < n_chunks; ++c) {
