@@ -59,6 +59,8 @@ struct q3_session {
   DBuf tr_ids, tr_proj;            // staging of q3_set_trailing_ids
   DBuf pf_tid, pf_cid;             // staging of q3_prefill_ids
   DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag;
+  std::vector<DBuf> m2_progs;      // cached full-frame program of every row group
+  std::vector<int> m2_group_nph;
   int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
   size_t m2_smem = 0, m3_smem = 0;
   DBuf prof;                       // optional timestamp buffer (q3_debug_profile)
@@ -401,11 +403,14 @@ static void mega_launch(q3_session* s, MegaArgs& a) {
 
 // ---- persistent frame kernel, dataflow generation (mega2.cuh) ---------------------------------------------
 // The phase program of one frame for the given mode; every pointer is resolved here, once.
+// Rows [r0, r0 + Bg) of the session form one launch group (batches above 16 run as groups of 16, back to back).
 static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_finish, bool do_talker, bool do_sample,
-                                             const bf16* ext_in, float* cp_logits) {
+                                             const bf16* ext_in, float* cp_logits, int r0 = 0, int Bg = -1) {
   const q3_model* m = s->m;
   const q3_model_desc& d = m->d;
-  const int B = s->B, G = s->mega_grid, H = d.hidden, C = d.cp_hidden;
+  const int Btot = s->B, G = s->mega_grid, H = d.hidden, C = d.cp_hidden;
+  const int B = Bg < 0 ? Btot : Bg;                               // rows of this group
+  unsigned long long* amax_g = s->fs.amax + (size_t)(r0 / MEGA_TMAX) * 15 * MEGA_TMAX;   // the group's arg-max keys [15][B]
   std::vector<M2Phase> pr;
   u64* xT = s->m2_x.as<u64>();
   u64* qkvT = s->m2_qkv.as<u64>();
@@ -441,8 +446,8 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
   auto layers = [&](const std::vector<LayerW>& L, const StackDims& dm, int T, int S, bool cp, int pos_add, bf16* kc, bf16* vc,
                     int cache_seq, int row0) {
     const int nh = dm.heads + 2 * dm.kv_heads;
-    const size_t layer_stride = (size_t)B * dm.kv_heads * cache_seq * 128;
-    const size_t row_off = (size_t)row0 * dm.kv_heads * cache_seq * 128;     // first batch row of this group in the caches
+    const size_t layer_stride = (size_t)Btot * dm.kv_heads * cache_seq * 128;
+    const size_t row_off = (size_t)(r0 + row0) * dm.kv_heads * cache_seq * 128;   // first batch row of this group in the caches
     for (int l = 0; l < dm.layers; ++l) {
       const LayerW& w = samew ? L[0] : L[l];    // Q3_DEBUG_SAMEW=1: timing experiment with L2-resident weights (wrong results)
       M2Phase q = blank(M2_GEMV);      // rms_norm(x) -> [q;k;v]
@@ -500,7 +505,7 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
         h.xf = XF_BF16T;
         h.X = g == 0 ? (const void*)(reinterpret_cast<const char*>(xT) + (size_t)C * 4) : (const void*)xT;
         h.ldx = g == 0 ? 2 * C : C;
-        h.epi = EPI_LOGITS; h.amax = s->fs.amax + (size_t)g * B + row0;
+        h.epi = EPI_LOGITS; h.amax = amax_g + (size_t)g * B + row0;
         h.Yf = cp_logits ? cp_logits + ((size_t)g * B + row0) * d.cp_vocab : nullptr;
         pick_small(h); pr.push_back(h);
       }
@@ -520,7 +525,8 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
     layers(m->tl, m->tdims(), B, 1, false, 0, s->tk_k.as<bf16>(), s->tk_v.as<bf16>(), s->max_seq, 0);
     M2Phase h = blank(M2_GEMV);
     h.W = m->codec_head; h.N = d.codec_vocab; h.K = H; h.T = B; h.flags = PF_NORM | PF_ARRIVE_REL; h.aux = m->t_norm;
-    h.xf = XF_BF16T; h.X = xT; h.ldx = H; h.xn_out = s->fs.last_hidden; h.epi = EPI_LOGITS; h.Yf = s->logits.as<float>();
+    h.xf = XF_BF16T; h.X = xT; h.ldx = H; h.xn_out = s->fs.last_hidden + (size_t)r0 * H; h.epi = EPI_LOGITS;
+    h.Yf = s->logits.as<float>() + (size_t)r0 * d.codec_vocab;
     pick_small(h); pr.push_back(h);
   }
   if (do_sample) {
@@ -531,22 +537,32 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
   return pr;
 }
 
-static M2Args mega2_args(q3_session* s) {
+static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   const q3_model* m = s->m;
   const q3_model_desc& d = m->d;
   M2Args a;
   memset(&a, 0, sizeof(a));
-  a.B = s->B; a.H = d.hidden; a.n_ac = d.groups - 1; a.eps = d.rms_eps;
+  if (Bg < 0) Bg = s->B;
+  a.B = Bg; a.H = d.hidden; a.n_ac = d.groups - 1; a.eps = d.rms_eps;
   a.fs = s->fs;
+  {
+    // per-row state of the group: every array shifted to its first row
+    FrameState& f = a.fs;
+    const size_t V = d.codec_vocab, H = d.hidden;
+    f.cur_tok += r0; f.done += r0; f.n_frames += r0; f.token_count += r0; f.offset += r0; f.frame_idx += r0; f.rng += r0;
+    f.seen += (size_t)r0 * V; f.last_hidden += (size_t)r0 * H; f.trailing += (size_t)r0 * f.lt_max * H; f.lt += r0;
+    f.codes += (size_t)r0 * f.frames_cap * 16; f.frame_codes += (size_t)r0 * 16;
+    f.amax += (size_t)(r0 / MEGA_TMAX) * 15 * MEGA_TMAX;
+  }
   a.cp_cos = m->cp_cos; a.cp_sin = m->cp_sin; a.t_cos = s->cos_tab.as<bf16>(); a.t_sin = s->sin_tab.as<bf16>();
   a.max_seq = s->max_seq; a.cp_max_seq = d.cp_max_seq;
   a.codec_emb = m->codec_emb;
   for (int i = 0; i < 15; ++i) a.cp_emb[i] = m->cp_emb[i];
-  a.step_input = s->step_input.as<bf16>();
-  SampleArgs sa = make_sample_args(s->cfg, d.codec_vocab, s->B);
-  sa.logits = s->logits.as<float>();
-  sa.seen = s->fs.seen; sa.rng = s->fs.rng; sa.tok_out = s->fs.cur_tok; sa.token_count = s->fs.token_count;
-  sa.done = s->fs.done; sa.offset = s->fs.offset; sa.frame_idx = s->fs.frame_idx; sa.host_flags = nullptr; sa.advance = 1;
+  a.step_input = s->step_input.as<bf16>() + (size_t)r0 * d.hidden;
+  SampleArgs sa = make_sample_args(s->cfg, d.codec_vocab, Bg);
+  sa.logits = s->logits.as<float>() + (size_t)r0 * d.codec_vocab;
+  sa.seen = a.fs.seen; sa.rng = a.fs.rng; sa.tok_out = a.fs.cur_tok; sa.token_count = a.fs.token_count;
+  sa.done = a.fs.done; sa.offset = a.fs.offset; sa.frame_idx = a.fs.frame_idx; sa.host_flags = nullptr; sa.advance = 1;
   a.smp = sa;
   a.bar = s->bar.as<unsigned>();
   a.tag_ctr = s->m2_tag.as<unsigned>();
@@ -604,21 +620,33 @@ static void mega2_run_mode(q3_session* s, bool do_cp, bool do_finish, bool do_ta
 }
 
 static void run_frames_mega2(q3_session* s, int n) {
+  // row groups of at most MEGA_TMAX rows, each with its own cached phase program
+  const int n_groups = (s->B + MEGA_TMAX - 1) / MEGA_TMAX;
   if (s->m2_n_ph == 0) {
-    std::vector<M2Phase> pr = m2_build_program(s, true, true, true, true, nullptr, nullptr);
-    s->m2_prog.ensure(pr.size() * sizeof(M2Phase));
-    Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_prog.p, pr.data(), pr.size() * sizeof(M2Phase), cudaMemcpyHostToDevice, s->st));
-    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
-    s->m2_n_ph = (int)pr.size();
+    s->m2_progs.clear();
+    s->m2_progs.resize(n_groups);
+    s->m2_group_nph.assign(n_groups, 0);
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const int r0 = gi * MEGA_TMAX, Bg = std::min(MEGA_TMAX, s->B - r0);
+      std::vector<M2Phase> pr = m2_build_program(s, true, true, true, true, nullptr, nullptr, r0, Bg);
+      s->m2_progs[gi].ensure(pr.size() * sizeof(M2Phase));
+      Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_progs[gi].p, pr.data(), pr.size() * sizeof(M2Phase), cudaMemcpyHostToDevice, s->st));
+      Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+      s->m2_group_nph[gi] = (int)pr.size();
+    }
+    s->m2_n_ph = s->m2_group_nph[0];
   }
   const int per_launch = 16;
   int done_frames = 0, blk = 0;
   bool stop = false;
   while (done_frames < n && !stop) {
     const int todo = std::min(per_launch, n - done_frames);
-    M2Args a = mega2_args(s);
-    a.n_frames = todo; a.do_sample = 1;
-    mega2_launch(s, a, s->m2_prog, s->m2_n_ph);
+    for (int gi = 0; gi < n_groups; ++gi) {
+      const int r0 = gi * MEGA_TMAX, Bg = std::min(MEGA_TMAX, s->B - r0);
+      M2Args a = mega2_args(s, r0, Bg);
+      a.n_frames = todo; a.do_sample = 1;
+      mega2_launch(s, a, s->m2_progs[gi], s->m2_group_nph[gi]);
+    }
     done_frames += todo;
     count_active_kernel<<<1, 32, 0, s->st>>>(s->fs.done, s->B, s->host_flags_dev + (blk & 1));
     Q3_COUNT_LAUNCH();
@@ -993,7 +1021,7 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
   s->last_hidden.alloc((size_t)B * H * 2); s->tts_pad.alloc((size_t)H * 2); s->lt.alloc(B * 4);
   s->trailing.alloc((size_t)B * H * 2);
   s->codes.alloc((size_t)B * s->frames_cap * 16 * 4);
-  s->amax.alloc((size_t)15 * B * 8); s->frame_codes.alloc((size_t)B * 16 * 4);
+  s->amax.alloc((size_t)15 * std::max(B, MEGA_TMAX * ((B + MEGA_TMAX - 1) / MEGA_TMAX)) * 8); s->frame_codes.alloc((size_t)B * 16 * 4);
   s->logits.alloc((size_t)B * V * 4); s->step_input.alloc((size_t)B * H * 2);
   s->cp_x0.alloc((size_t)2 * B * H * 2); s->cp_xe.alloc((size_t)B * H * 2);
   s->lens_dev.alloc(B * 4);
@@ -1031,14 +1059,14 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
     const bool dims_ok = d.layers + d.cp_layers <= MEGA_MAX_LAYERS && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 && d.inter % 32 == 0 &&
                          d.cp_inter % 32 == 0 && d.codec_vocab % 16 == 0 && d.cp_vocab % 16 == 0;
     // the dataflow generation also takes batches 9..16 (code-predictor pass 0 in two row groups)
-    if (want && s->mega_ver == 2 && dims_ok && B <= MEGA_TMAX) {
+    if (want && s->mega_ver == 2 && dims_ok) {           // batches above 16 run as row groups of 16
       s->use_mega = true;
       s->mega_grid = m->num_sms;
     }
     if (s->use_mega && s->mega_ver == 2) {
       // dataflow generation: tagged activation buffers (8-byte slots), the phase program, the session's tag counter
       const int n_ph_max = 3 + (d.groups - 1 + (B > 8 ? 1 : 0)) * (2 + 5 * d.cp_layers) + 1 + 5 * d.layers + 1;
-      s->m2_smem = mega2_smem_bytes(d, B, max_seq, m->num_sms, n_ph_max);
+      s->m2_smem = mega2_smem_bytes(d, std::min(B, (int)MEGA_TMAX), max_seq, m->num_sms, n_ph_max);
       int per_sm = 0;
       if (s->m2_smem > 0 && s->m2_smem <= 227 * 1024) {
         Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->m2_smem));
@@ -1056,7 +1084,7 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
         s->host_flags[4] = 0;
         // TMA weight ring (mega3.cuh): every skinny-GEMM phase must be one of its (K, format) combinations
         const bool want3 = env && env[0] == '3';     // experimental: slower than the dataflow kernel on B200
-        if (want3) {
+        if (want3 && B <= 8) {
           s->mega_grid = m->num_sms;
           std::vector<M2Phase> pr = m2_build_program(s.get(), true, true, true, true, nullptr, nullptr);
           bool ok3 = true;
@@ -1406,7 +1434,7 @@ q3_status q3_talker_step(q3_session* s, const uint16_t* step_input, uint16_t* hi
                                           " + new=1 > max=" + std::to_string(s->max_seq));
   ensure_scratch(s, 2 * s->B);
   bf16* x = s->sc.x.as<bf16>();
-  if (s->use_mega) {
+  if (s->use_mega && s->B <= MEGA_TMAX) {
     Q3_CHECK_CUDA(cudaMemcpyAsync(s->step_input.p, step_input, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
     if (s->mega_ver >= 2) {
       mega2_run_mode(s, false, false, true, false, s->step_input.as<bf16>(), nullptr);
@@ -1442,7 +1470,7 @@ q3_status q3_code_predictor_frame(q3_session* s, const uint16_t* last_hidden, co
   Q3_CHECK_CUDA(cudaMemcpyAsync(s->last_hidden.p, last_hidden, (size_t)B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
   Q3_CHECK_CUDA(cudaMemcpyAsync(s->cur_tok.p, sem_tokens, B * 4, cudaMemcpyHostToDevice, s->st));
   if (logits_out) s->cp_logits.ensure((size_t)n_ac * B * d.cp_vocab * 4);
-  if (s->use_mega) {
+  if (s->use_mega && s->B <= MEGA_TMAX) {
     ensure_scratch(s, 2 * B);
     if (s->mega_ver >= 2) {
       mega2_run_mode(s, true, false, false, false, nullptr, logits_out ? s->cp_logits.as<float>() : nullptr);

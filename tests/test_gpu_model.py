@@ -199,23 +199,40 @@ def test_missing_weight_is_an_error():
 
 
 def test_multi_kernel_path_rows_independent_and_matches_oracle_tolerance(monkeypatch):
-    """The multi-kernel (CUDA-graph) decode path -- used for batch > 16 per GPU -- is kept honest: a batch of 20
-    (forced onto it by size) is bit-identical, row by row, to batch-1 runs forced onto the same path with Q3_MEGA=0,
-    and its forks from the oracle happen only at near-ties."""
+    """The multi-kernel (CUDA-graph) decode path -- the fallback when the persistent kernel cannot be used, and the
+    prefill engine -- is kept honest: with Q3_MEGA=0 a batch of 20 is bit-identical, row by row, to batch-1 runs on the
+    same path, and its forks from the oracle happen only at near-ties."""
     spec = S.SPEC_TINY_PROJ
     B, F = 20, 10
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(i, spec) for i in range(B)]
     seeds = [7 + i for i in range(B)]
     tts = gpu_tts(spec)
-    big = tts.generate_codes(prompts, options=opts, seeds=seeds)
     monkeypatch.setenv("Q3_MEGA", "0")
+    big = tts.generate_codes(prompts, options=opts, seeds=seeds)
     for i in (0, 5, 19):
         single = tts.generate_codes([prompts[i]], options=opts, seeds=[seeds[i]])[0]
         assert single == big[i], i
     ref, tr, _ = oracle_run(spec, prompts[2], seeds[2], opts, trace=True)
     m, ok, why = _first_divergence_is_a_near_tie(big[2], ref, tr)
     assert ok, (m, why)
+
+
+def test_batches_above_16_run_as_row_groups_on_the_persistent_kernel():
+    """Batch 37 = row groups of 16 + 16 + 5 launched back to back on the dataflow kernel: every row equals the batch-1
+    run with the same prompt and seed (bit-identical), including rows at group boundaries, and a second run repeats."""
+    spec = S.SPEC_MID
+    B, F = 37, 18
+    opts = api.SynthesisOptions(max_length=F)
+    prompts = [W.synthetic_prompt(60 + i, spec) for i in range(B)]
+    seeds = [900 + i for i in range(B)]
+    tts = gpu_tts(spec)
+    a = tts.generate_codes(prompts, options=opts, seeds=seeds)
+    assert a == tts.generate_codes(prompts, options=opts, seeds=seeds)
+    assert all(len(r) == F for r in a)
+    for i in (0, 15, 16, 31, 32, 36):
+        single = tts.generate_codes([prompts[i]], options=opts, seeds=[seeds[i]])[0]
+        assert single == a[i], i
 
 
 def test_full_size_1p7b_batch8_properties():
