@@ -8,27 +8,61 @@
 
 #include "common.cuh"
 
+// Size-keyed cache of freed device buffers (per device).  A session allocates ~40 buffers (0.5 GB of KV cache at
+// batch 8 / 512 positions) and the reference-style API creates one session per synthesize call; cudaMalloc/cudaFree
+// of those cost 100-400 ms per call and serialise the device.  Buffers come back in an undefined state: callers that
+// need zeros call zero() (they already did).  A buffer is only released after its session's stream was synchronised.
+struct DevPool {
+  std::mutex mu;
+  std::multimap<std::pair<int, size_t>, void*> free_;
+  size_t cached = 0;
+  static constexpr size_t kLimit = (size_t)24 << 30;
+  static DevPool& get() { static DevPool p; return p; }
+  void* take(int dev, size_t n) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = free_.find({dev, n});
+    if (it == free_.end()) return nullptr;
+    void* p = it->second;
+    free_.erase(it);
+    cached -= n;
+    return p;
+  }
+  bool give(int dev, void* p, size_t n) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cached + n > kLimit) return false;
+    free_.emplace(std::make_pair(dev, n), p);
+    cached += n;
+    return true;
+  }
+};
+
 struct DBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  int dev = 0;
   DBuf() = default;
   DBuf(const DBuf&) = delete;
   DBuf& operator=(const DBuf&) = delete;
-  DBuf(DBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DBuf(DBuf&& o) noexcept : p(o.p), bytes(o.bytes), dev(o.dev) { o.p = nullptr; o.bytes = 0; }
   DBuf& operator=(DBuf&& o) noexcept {
-    if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+    if (this != &o) { release(); p = o.p; bytes = o.bytes; dev = o.dev; o.p = nullptr; o.bytes = 0; }
     return *this;
   }
   ~DBuf() { release(); }
   void alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    Q3_CHECK_CUDA(cudaMalloc(&p, n));
+    Q3_CHECK_CUDA(cudaGetDevice(&dev));
+    p = DevPool::get().take(dev, n);
+    if (p == nullptr) Q3_CHECK_CUDA(cudaMalloc(&p, n));
     bytes = n;
   }
   void ensure(size_t n) { if (n > bytes) alloc(n); }
   void zero(cudaStream_t st = 0) { if (p) Q3_CHECK_CUDA(cudaMemsetAsync(p, 0, bytes, st)); }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() {
+    if (p && !DevPool::get().give(dev, p, bytes)) cudaFree(p);
+    p = nullptr; bytes = 0;
+  }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -74,6 +108,13 @@ struct VocoderWorkspace {
   DBuf codes, e_first, e_rest, a, b, c, d, qh, kh, vh;
 };
 
+// Vocoder scratch of one session (multi-GB at 256 frames x 8 rows).  Sessions borrow it from the model's pool and hand
+// it back when they are destroyed: a cudaMalloc + cudaFree of these buffers per synthesize call cost ~0.7 s.
+struct VocoderScratch {
+  VocoderWorkspace ws;
+  DBuf codes, pcm;
+};
+
 struct q3_model {
   q3_model_desc d;
   int num_sms = 148;
@@ -95,6 +136,22 @@ struct q3_model {
   VocoderW voc;
   mutable std::mutex voc_mutex;          // guards voc_ws for the session-less q3_vocoder_decode
   mutable VocoderWorkspace voc_ws;
+  mutable std::mutex pool_mutex;
+  mutable std::vector<std::unique_ptr<VocoderScratch>> voc_pool;   // idle scratch objects (at most 4 are kept)
+  std::unique_ptr<VocoderScratch> acquire_scratch() const {
+    std::lock_guard<std::mutex> lock(pool_mutex);
+    if (!voc_pool.empty()) {
+      std::unique_ptr<VocoderScratch> r = std::move(voc_pool.back());
+      voc_pool.pop_back();
+      return r;
+    }
+    return std::unique_ptr<VocoderScratch>(new VocoderScratch());
+  }
+  void release_scratch(std::unique_ptr<VocoderScratch> v) const {
+    if (!v) return;
+    std::lock_guard<std::mutex> lock(pool_mutex);
+    if (voc_pool.size() < 4) voc_pool.push_back(std::move(v));
+  }
   StackDims tdims() const { return {d.hidden, d.inter, d.heads, d.kv_heads, d.layers}; }
   StackDims cdims() const { return {d.cp_hidden, d.cp_inter, d.cp_heads, d.cp_kv_heads, d.cp_layers}; }
 };

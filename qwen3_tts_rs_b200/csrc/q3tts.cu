@@ -73,8 +73,7 @@ struct q3_session {
   uint64_t graph_launches = 0;     // kernels inside one replay of the frame graph
   // streaming
   std::vector<int> stream_emitted;
-  VocoderWorkspace voc_ws;
-  DBuf voc_codes, voc_pcm;
+  std::unique_ptr<VocoderScratch> voc;   // borrowed from the model's pool at the first vocode, returned on destruction
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
   q3_timing timing{};
@@ -85,6 +84,7 @@ struct q3_session {
     for (auto& e : ev_poll) if (e) cudaEventDestroy(e);
     if (host_flags) cudaFreeHost(host_flags);
     if (st) cudaStreamDestroy(st);
+    if (m && voc) m->release_scratch(std::move(voc));
   }
 };
 
@@ -1112,6 +1112,9 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
   fs.trailing = s->trailing.as<bf16>(); fs.lt = s->lt.as<int>(); fs.lt_max = 1; fs.tts_pad = s->tts_pad.as<bf16>();
   fs.codes = s->codes.as<uint32_t>(); fs.frames_cap = s->frames_cap; fs.amax = s->amax.as<unsigned long long>();
   fs.frame_codes = s->frame_codes.as<uint32_t>(); fs.host_flags = s->host_flags_dev;
+  // the zero-fills above went to the legacy default stream, the session works on its own non-blocking stream, and
+  // recycled buffers (DevPool) may hold a previous session's data: order them explicitly
+  Q3_CHECK_CUDA(cudaStreamSynchronize(0));
   reset_state(s.get(), seeds);
   *out = s.release();
   Q3_API_END
@@ -1319,16 +1322,19 @@ static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& ro
   const q3_model* m = s->m;
   const int B = s->B, up = vocoder_total_upsample(m);
   if (T <= 0) return;
-  s->voc_codes.ensure((size_t)B * 16 * T * 8);
-  s->voc_pcm.ensure((size_t)B * T * up * 4);
+  if (!s->voc) s->voc = m->acquire_scratch();
+  DBuf& voc_codes = s->voc->codes;
+  DBuf& voc_pcm = s->voc->pcm;
+  voc_codes.ensure((size_t)B * 16 * T * 8);
+  voc_pcm.ensure((size_t)B * T * up * 4);
   // rows decode independently (the vocoder is causal per row), so one batched call over T frames and a
   // per-row truncation reproduces B separate Decoder12Hz::decode calls of length row_len[b].
-  vocoder_codes_to_tensor(s->codes.as<uint32_t>(), s->frames_cap, f0, T, B, s->voc_codes.as<long long>(), s->st);
-  vocoder_run(m, s->voc_ws, s->voc_codes.as<long long>(), B, T, s->voc_pcm.as<float>(), s->st);
+  vocoder_codes_to_tensor(s->codes.as<uint32_t>(), s->frames_cap, f0, T, B, voc_codes.as<long long>(), s->st);
+  vocoder_run(m, s->voc->ws, voc_codes.as<long long>(), B, T, voc_pcm.as<float>(), s->st);
   if (pcm_host) {
     for (int b = 0; b < B; ++b) {
       const size_t n = (size_t)row_len[b] * up;
-      if (n) Q3_CHECK_CUDA(cudaMemcpyAsync(pcm_host + b * pcm_row_stride, s->voc_pcm.as<float>() + (size_t)b * T * up, n * 4,
+      if (n) Q3_CHECK_CUDA(cudaMemcpyAsync(pcm_host + b * pcm_row_stride, voc_pcm.as<float>() + (size_t)b * T * up, n * 4,
                                            cudaMemcpyDeviceToHost, s->st));
     }
     Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
