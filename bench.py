@@ -86,9 +86,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# one `ncu --set full` capture of decode_frames_mega2_kernel at the bench shape (1.7B, batch 8): 73.39 GB read +
-# 0.50 GB written per 16-frame launch
-NCU_TRAFFIC_PER_FRAME = (73.394839e9 + 0.497831e9) / 16.0
+# one `ncu --set full` capture of decode_frames_mega2_kernel at the bench shape (1.7B, batch 8): 73.30 GB read +
+# 0.42 GB written per 16-frame launch (profiles/r1_mega2_full.summary.txt)
+NCU_TRAFFIC_PER_FRAME = (73.301614e9 + 0.415258e9) / 16.0
 
 
 def measured_peaks():
