@@ -1001,24 +1001,25 @@ __device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned
           }
         }
         m2_csync();
+        // softmax of the (<= 16) scores of head h by warp h, one position per lane; probabilities (rounded to bf16 as the
+        // reference's softmax output is) go back into the score array
+        if (warp < 2) {
+          float* sc = warp == 0 ? sc0 : sc1;
+          const float x = lane < L ? sc[lane] : -INFINITY;
+          const float m = warp_max(x);
+          const float e = lane < L ? expf(x - m) : 0.f;
+          const float sum = warp_sum_xor(e);
+          if (lane < L) sc[lane] = rbf(e / sum);
+        }
+        m2_csync();
         float outv = 0.f;
         const int h = (tid >> 7) & 1, d = tid & 127;
         if (tid < 256) {
-          // every thread evaluates the (<= 16-entry) softmax of its head itself, in position order
           const float* sc = h == 0 ? sc0 : sc1;
-          float m = -INFINITY;
-          for (int j = 0; j < L; ++j) m = fmaxf(m, sc[j]);
-          float e[M2_ATT_FAST_L];
-          float sum = 0.f;
-#pragma unroll
-          for (int j = 0; j < M2_ATT_FAST_L; ++j) {
-            e[j] = j < L ? expf(sc[j] - m) : 0.f;
-            sum += e[j];
-          }
           float acc = 0.f;
 #pragma unroll
           for (int j = 0; j < M2_ATT_FAST_L; ++j)
-            if (j < L) acc = fmaf(rbf(e[j] / sum), bf2f(Vs[j * 128 + d]), acc);
+            if (j < L) acc = fmaf(sc[j], bf2f(Vs[j * 128 + d]), acc);
           outv = rbf(acc);
         }
         const float other = __shfl_xor_sync(0xffffffffu, outv, 1);
