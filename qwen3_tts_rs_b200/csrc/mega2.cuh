@@ -426,7 +426,6 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
   const bool write_xn = NORM && p.xn_out != nullptr && blockIdx.x == 0;
 
   float rres[MEGA_MAX_OUT];
-  m2_load_residual(p, r0, r1, rres);
 
   uint4 wl[NM][JU], wh[NM][JU];
   auto load_w = [&](int tile, int c) {
@@ -461,7 +460,8 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
       }
     }
   };
-  // ---- before the wait: first weights, residual rows, (XRES) the norm weights ----
+  // ---- before the wait: first weights, (XRES) the norm weights, then the residual rows (their conversion waits for
+  // the data, so they come last) ----
   load_w(0, 0);
   uint4 wnr[XC][JU];
   if constexpr (XRES) {
@@ -473,6 +473,7 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
         if (c < n_chunks) wnr[c][u] = *reinterpret_cast<const uint4*>(p.aux + koff0 + (c * JU + u) * 512);
       }
   }
+  m2_load_residual(p, r0, r1, rres);
   m2_wait(gs, p.flags);
   prof2(a, 2);
   m2_stamp(gs, 0);
@@ -702,8 +703,7 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
   const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
   const int koff0 = warp * 32 + 8 * tg;
   float rres[MEGA_MAX_OUT];
-  m2_load_residual(p, r0, r1, rres);
-  // ---- before the wait: every weight fragment of the phase, the norm weights ----
+  // ---- before the wait: every weight fragment of the phase, the norm weights, then the residual rows ----
   uint4 wl[TILES][CHUNKS][NM][JU], wh[TILES][CHUNKS][NM][JU];
 #pragma unroll
   for (int tile = 0; tile < TILES; ++tile) {
@@ -734,6 +734,7 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
 #pragma unroll
       for (int u = 0; u < JU; ++u) wn[c][u] = *reinterpret_cast<const uint4*>(p.aux + koff0 + (c * JU + u) * 512);
   }
+  m2_load_residual(p, r0, r1, rres);
   m2_wait(gs, p.flags);
   prof2(a, 2);
   m2_stamp(gs, 0);
