@@ -298,10 +298,11 @@ __device__ __forceinline__ void m2_tail(const M2Args& a, const M2Phase& p, const
                                         const uint32_t tag) {
   constexpr int NM = DUAL ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, T = p.T;
+  const bool prof_on = a.prof != nullptr;
   const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
-  m2_stamp(gs, 2);
+  if (prof_on) m2_stamp(gs, 2);
   m2_csync();
-  prof2(a, 4);
+  if (prof_on) prof2(a, 4);
 #pragma unroll
   for (int it = 0; it < MEGA_MAX_OUT; ++it) {
     const int idx = tid + it * MEGA_THREADS;
@@ -351,7 +352,7 @@ __device__ __forceinline__ void m2_tail(const M2Args& a, const M2Phase& p, const
   }
   m2_csync();
   m2_arrive(gs, p.flags);
-  prof2(a, 5);
+  if (prof_on) prof2(a, 5);
   m2_prefetch(a, nx);
 }
 
@@ -402,6 +403,7 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
   float* part_s = reinterpret_cast<float*>(smem) + 16;
   float* red = reinterpret_cast<float*>(smem + M2_RED_OFF);
   const int K = p.K, T = p.T;
+  const bool prof_on = a.prof != nullptr;      // one shared-memory read instead of one per stamp
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const uint32_t xtag = tag - 1u;
   int r0, r1;
@@ -412,7 +414,7 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
     m2_prefetch(a, nx);
     return;
   }
-  prof2(a, 1);
+  if (prof_on) prof2(a, 1);
   constexpr int NM = DUAL ? 2 : 1;
   constexpr int JU = 2;
   constexpr int XC = XRES ? 2 : 1;
@@ -475,8 +477,8 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
   }
   m2_load_residual(p, r0, r1, rres);
   m2_wait(gs, p.flags);
-  prof2(a, 2);
-  m2_stamp(gs, 0);
+  if (prof_on) prof2(a, 2);
+  if (prof_on) m2_stamp(gs, 0);
   const char* xrow[NT];
   m2_token_rows<NT, XF>(a, p, g, xrow);
 
@@ -594,8 +596,8 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
   constexpr bool PLAIN = !NORM && XF == XF_GATHER;
   if constexpr (RAW) load_x_raw(0);
   if constexpr (PLAIN) load_x_plain(0);
-  prof2(a, 3);
-  m2_stamp(gs, 1);
+  if (prof_on) prof2(a, 3);
+  if (prof_on) m2_stamp(gs, 1);
   float acc[NM][NT][4];
   for (int tile = 0; tile < n_tiles; ++tile) {
 #pragma unroll
@@ -686,6 +688,7 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
   float* part_s = reinterpret_cast<float*>(smem) + 16;
   float* red = reinterpret_cast<float*>(smem + M2_RED_OFF);
   const int K = p.K;
+  const bool prof_on = a.prof != nullptr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const uint32_t xtag = tag - 1u;
   constexpr int NM = DUAL ? 2 : 1;
@@ -698,7 +701,7 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
     m2_prefetch(a, nx);
     return;
   }
-  prof2(a, 1);
+  if (prof_on) prof2(a, 1);
   const int n_tiles = (r1 - r0 + 15) >> 4;
   const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
   const int koff0 = warp * 32 + 8 * tg;
@@ -736,8 +739,8 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
   }
   m2_load_residual(p, r0, r1, rres);
   m2_wait(gs, p.flags);
-  prof2(a, 2);
-  m2_stamp(gs, 0);
+  if (prof_on) prof2(a, 2);
+  if (prof_on) m2_stamp(gs, 0);
   // ---- after the wait: activations (once, tag-verified), scales ----
   const char* xrow[NT];
   m2_token_rows<NT, XF>(a, p, g, xrow);
@@ -778,8 +781,8 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
             *reinterpret_cast<uint4*>(p.xn_out + (size_t)(nt * 8 + g) * K + koff0 + (c * JU + u) * 512) = xv[c][u][nt];
         }
   }
-  prof2(a, 3);
-  m2_stamp(gs, 1);
+  if (prof_on) prof2(a, 3);
+  if (prof_on) m2_stamp(gs, 1);
 #pragma unroll
   for (int tile = 0; tile < TILES; ++tile) {
     if (tile < n_tiles) {
@@ -878,6 +881,7 @@ __device__ __forceinline__ void m2_gemv_dispatch(const M2Args& a, const M2Phase&
 constexpr int M2_ATT_FAST_L = 16;
 __device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync& gs, const uint32_t tag) {
   const bool cp = (p.flags & PF_CP) != 0;
+  const bool prof_on = a.prof != nullptr;
   const int max_seq = cp ? a.cp_max_seq : a.max_seq;
   const bf16* cos_tab = cp ? a.cp_cos : a.t_cos;
   const bf16* sin_tab = cp ? a.cp_sin : a.t_sin;
@@ -904,8 +908,8 @@ __device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned
     pos0 = (pos_base ? __ldcg(pos_base + b0) : 0) + p.pos_add;
   }
   m2_wait(gs, p.flags);
-  prof2(a, 6);
-  m2_stamp(gs, 0);
+  if (prof_on) prof2(a, 6);
+  if (prof_on) m2_stamp(gs, 0);
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int b = item / kv_heads, kvh = item - b * kv_heads;
     bf16* kbase = const_cast<bf16*>(p.W) + ((size_t)b * kv_heads + kvh) * max_seq * 128;
@@ -1117,7 +1121,7 @@ __device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned
   }
   m2_csync();
   m2_arrive(gs, p.flags);
-  prof2(a, 7);
+  if (prof_on) prof2(a, 7);
 }
 
 // ---------------------------------------------------------------------------------------------------
