@@ -35,7 +35,7 @@ enum M2Kind { M2_GEMV = 0, M2_ATTN = 1, M2_PROLOGUE = 2, M2_GATHER = 3, M2_FINIS
 enum M2Fmt { XF_BF16T = 0, XF_F32T = 1, XF_GATHER = 2, XF_NONE = 3 };
 enum M2Flags { PF_WAIT_ACQ = 1, PF_ARRIVE_REL = 2, PF_DUAL = 4, PF_NORM = 8, PF_CP = 16, PF_CP0 = 32 };
 
-struct alignas(16) M2Phase {   // 144 bytes
+struct alignas(16) M2Phase {   // 160 bytes
   const bf16* W;        // GEMV: weights [N][K]; ATTN: K cache of the layer
   const bf16* W2;       // GEMV: dual partner; ATTN: V cache of the layer
   const void* X;        // tagged input (row of token t at X + t*ldx elements) ; COPYIN: plain bf16 [B][H]
@@ -50,8 +50,10 @@ struct alignas(16) M2Phase {   // 144 bytes
   int ldy, ldr, g, kind;
   int flags, epi, xf, small;   // small: (tiles << 4) | chunks of the register-resident variant, 0 = streaming variant
   int pos_add, S, rf, yf;
+  int next_gemv;        // index of the skinny-GEMM phase whose weight rows this phase prefetches into L2, or -1 (host-resolved)
+  int pad_[3];
 };
-static_assert(sizeof(M2Phase) == 144, "M2Phase layout");
+static_assert(sizeof(M2Phase) == 160, "M2Phase layout");
 
 struct M2Args {
   const M2Phase* prog;
@@ -1176,6 +1178,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega2_kernel(co
     return;
   }
   const uint32_t tag0 = __ldcg(a.tag_ctr);
+  const bool prof_any = a.prof != nullptr;
   uint32_t seq = 0;
   bool stop = false;
   m2_arrive(gs, PF_ARRIVE_REL);       // every phase waits for its predecessor's arrive; this is the first phase's
@@ -1183,7 +1186,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega2_kernel(co
     for (int i = 0; i < a.n_ph; ++i) {
       const M2Phase& p = prog[i];
       seq += 1u;
-      if (a.prof_mode == 2) {
+      if (prof_any && a.prof_mode == 2) {
         gs.arr = frame == 1 ? a.prof + (size_t)i * 4 * gridDim.x : nullptr;
         gs.retries = frame == 1 ? reinterpret_cast<unsigned*>(a.prof + (size_t)a.n_ph * 4 * gridDim.x) + i : nullptr;
         if (frame == 1 && i == 0 && threadIdx.x == 0) {
@@ -1198,17 +1201,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega2_kernel(co
       // rows (the largest matrix of a layer) are requested at the START of the attention phase, two phases ahead;
       // o_proj itself then prefetches nothing.  (Measured before this change: the talker gate/up phase spent 5.7 us
       // in its wait while the 50 MB prefetch issued at the end of o_proj drained, then streamed from L2.)
-      const M2Phase* nx = nullptr;
-      {
-        int j = i + 1 < a.n_ph ? i + 1 : 0;
-        if (prog[j].kind != M2_GEMV) j = j + 1 < a.n_ph ? j + 1 : 0;
-        if (prog[j].kind == M2_GEMV && (j > i || frame + 1 < a.n_frames)) nx = &prog[j];
-        if (a.prefetch == 2 && i > 0 && prog[i - 1].kind == M2_ATTN) nx = nullptr;
-      }
+      // (the prefetch plan is resolved on the host: M2Phase::next_gemv)
+      const int nxi = p.next_gemv;
+      const M2Phase* nx = (nxi >= 0 && (nxi > i || frame + 1 < a.n_frames)) ? &prog[nxi] : nullptr;
       switch (p.kind) {
         case M2_GEMV: m2_gemv_dispatch(a, p, nx, work, gs, tag); break;
         case M2_ATTN:
-          if (a.prefetch == 2 && i + 2 < a.n_ph && prog[i + 2].kind == M2_GEMV) m2_prefetch(a, &prog[i + 2]);
+          m2_prefetch(a, nx);
           m2_attn(a, p, work, gs, tag);
           break;
         case M2_PROLOGUE: {

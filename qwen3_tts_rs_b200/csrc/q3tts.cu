@@ -534,6 +534,26 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
     sp.flags = PF_WAIT_ACQ | PF_ARRIVE_REL;
     pr.push_back(sp);
   }
+  // L2 prefetch plan (Q3_PREFETCH: 0 none, 1 the next skinny-GEMM phase's rows at the end of every GEMV phase,
+  // 2 (default) additionally: the attention phase requests the gate/up rows two phases ahead at its start and the
+  // o_proj phase that follows requests nothing)
+  {
+    const char* e2 = std::getenv("Q3_PREFETCH");
+    const int mode = e2 ? std::atoi(e2) : 2;
+    const int n = (int)pr.size();
+    for (int i = 0; i < n; ++i) {
+      pr[i].next_gemv = -1;
+      if (mode == 0) continue;
+      if (pr[i].kind == M2_GEMV) {
+        int j = (i + 1) % n;
+        if (pr[j].kind != M2_GEMV) j = (j + 1) % n;
+        if (pr[j].kind == M2_GEMV) pr[i].next_gemv = j;
+        if (mode == 2 && i > 0 && pr[i - 1].kind == M2_ATTN) pr[i].next_gemv = -1;
+      } else if (pr[i].kind == M2_ATTN && mode == 2) {
+        if (i + 2 < n && pr[i + 2].kind == M2_GEMV) pr[i].next_gemv = i + 2;
+      }
+    }
+  }
   return pr;
 }
 
@@ -568,7 +588,7 @@ static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   a.tag_ctr = s->m2_tag.as<unsigned>();
   a.err = s->host_flags_dev + 4;
   const char* e2 = std::getenv("Q3_PREFETCH");
-  a.prefetch = e2 ? std::atoi(e2) : 2;      // 0: none, 1: next phase's rows at phase end, 2: + gate/up rows at attention start
+  a.prefetch = e2 ? (std::atoi(e2) != 0) : 1;      // the plan itself is part of the program (m2_build_program)
   const char* e3 = std::getenv("Q3_PF_SLEEP");
   a.pf_sleep = e3 ? std::atoi(e3) : 200;
   const char* e4 = std::getenv("Q3_RING_SHIFT");
