@@ -135,6 +135,15 @@ __device__ __forceinline__ void m2_fail(M2Sync& gs, int code) {
   if (gs.err != nullptr) atomicCAS(gs.err, 0, code);
   gs.dead = true;
 }
+// The phase functions take the sync state BY VALUE and return (epoch | dead << 32): passed by reference to a
+// non-inlined function it lived in local memory, and thread 0 paid a chain of LDL/STL round trips per phase.
+__device__ __forceinline__ unsigned long long m2_pack(const M2Sync& gs) {
+  return (unsigned long long)gs.epoch | ((unsigned long long)(gs.dead ? 1u : 0u) << 32);
+}
+__device__ __forceinline__ void m2_unpack(M2Sync& gs, unsigned long long r) {
+  gs.epoch = (unsigned)r;
+  gs.dead = (r >> 32) != 0ull;
+}
 // Every CTA executes one wait and one arrive per phase.  Relaxed form = hint only (tags carry the data
 // dependence); acquire/release form = real grid barrier for phases with untagged inputs/outputs.
 __device__ __forceinline__ void m2_wait(M2Sync& gs, int flags) {
@@ -400,8 +409,8 @@ constexpr int M2_RED_OFF = (16 + 256) * 4;
 // streamed through registers (two k-steps per warp in flight), the first chunk requested before the wait.
 // XRES (NORM only, K a multiple of 1024 and <= 2048): the activations stay in registers after the scale pass.
 template <bool DUAL, int NT, int XF, bool NORM, bool XRES>
-__device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2Phase* nx, unsigned char* smem, M2Sync& gs,
-                                     const uint32_t tag) {
+__device__ __noinline__ unsigned long long m2_gemv(const M2Args& a, const M2Phase& p, const M2Phase* nx, unsigned char* smem,
+                                                   M2Sync gs, const uint32_t tag) {
   float* part_s = reinterpret_cast<float*>(smem) + 16;
   float* red = reinterpret_cast<float*>(smem + M2_RED_OFF);
   const int K = p.K, T = p.T;
@@ -414,7 +423,7 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
     m2_wait(gs, p.flags);
     m2_arrive(gs, p.flags);
     m2_prefetch(a, nx);
-    return;
+    return m2_pack(gs);
   }
   if (prof_on) prof2(a, 1);
   constexpr int NM = DUAL ? 2 : 1;
@@ -679,14 +688,15 @@ __device__ __noinline__ void m2_gemv(const M2Args& a, const M2Phase& p, const M2
       }
   }
   m2_tail<DUAL, NT>(a, p, nx, red, rres, r0, r1, n_tiles, gs, tag);
+  return m2_pack(gs);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // Register-resident variant: K == CHUNKS * 1024 and at most TILES 16-row tiles per CTA, so ALL of a lane's
 // weight fragments (<= 16 x 128 bit) are requested before the wait; after it the activations are fetched once.
 template <bool DUAL, int NT, int XF, bool NORM, int TILES, int CHUNKS>
-__device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, const M2Phase* nx, unsigned char* smem,
-                                           M2Sync& gs, const uint32_t tag) {
+__device__ __noinline__ unsigned long long m2_gemv_small(const M2Args& a, const M2Phase& p, const M2Phase* nx,
+                                                         unsigned char* smem, M2Sync gs, const uint32_t tag) {
   float* part_s = reinterpret_cast<float*>(smem) + 16;
   float* red = reinterpret_cast<float*>(smem + M2_RED_OFF);
   const int K = p.K;
@@ -701,7 +711,7 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
     m2_wait(gs, p.flags);
     m2_arrive(gs, p.flags);
     m2_prefetch(a, nx);
-    return;
+    return m2_pack(gs);
   }
   if (prof_on) prof2(a, 1);
   const int n_tiles = (r1 - r0 + 15) >> 4;
@@ -817,60 +827,60 @@ __device__ __noinline__ void m2_gemv_small(const M2Args& a, const M2Phase& p, co
     }
   }
   m2_tail<DUAL, NT>(a, p, nx, red, rres, r0, r1, n_tiles, gs, tag);
+  return m2_pack(gs);
 }
 
 // variant dispatch (uniform over the grid: everything comes from the descriptor)
-__device__ __forceinline__ void m2_gemv_dispatch(const M2Args& a, const M2Phase& p, const M2Phase* nx, unsigned char* smem,
-                                                 M2Sync& gs, const uint32_t tag) {
+__device__ __forceinline__ unsigned long long m2_gemv_dispatch(const M2Args& a, const M2Phase& p, const M2Phase* nx,
+                                                               unsigned char* smem, const M2Sync& gs, const uint32_t tag) {
   const bool nt1 = p.T <= 8;
   const bool dual = (p.flags & PF_DUAL) != 0, norm = (p.flags & PF_NORM) != 0;
   const int sm = p.small;
   if (sm != 0) {
     if (dual) {             // gate/up: NORM, f32 input (h1)
-      if (nt1) m2_gemv_small<true, 1, XF_F32T, true, 2, 1>(a, p, nx, smem, gs, tag);
-      else m2_gemv_small<true, 2, XF_F32T, true, 2, 1>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv_small<true, 1, XF_F32T, true, 2, 1>(a, p, nx, smem, gs, tag);
+      else return m2_gemv_small<true, 2, XF_F32T, true, 2, 1>(a, p, nx, smem, gs, tag);
     } else if (norm) {
       if (sm == 0x21) {
-        if (nt1) m2_gemv_small<false, 1, XF_BF16T, true, 2, 1>(a, p, nx, smem, gs, tag);
-        else m2_gemv_small<false, 2, XF_BF16T, true, 2, 1>(a, p, nx, smem, gs, tag);
+        if (nt1) return m2_gemv_small<false, 1, XF_BF16T, true, 2, 1>(a, p, nx, smem, gs, tag);
+        else return m2_gemv_small<false, 2, XF_BF16T, true, 2, 1>(a, p, nx, smem, gs, tag);
       } else {              // 0x22, T <= 8 only
-        m2_gemv_small<false, 1, XF_BF16T, true, 2, 2>(a, p, nx, smem, gs, tag);
+        return m2_gemv_small<false, 1, XF_BF16T, true, 2, 2>(a, p, nx, smem, gs, tag);
       }
     } else if (p.xf == XF_GATHER) {
-      if (nt1) m2_gemv_small<false, 1, XF_GATHER, false, 1, 2>(a, p, nx, smem, gs, tag);
-      else m2_gemv_small<false, 2, XF_GATHER, false, 1, 2>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv_small<false, 1, XF_GATHER, false, 1, 2>(a, p, nx, smem, gs, tag);
+      else return m2_gemv_small<false, 2, XF_GATHER, false, 1, 2>(a, p, nx, smem, gs, tag);
     } else if (sm == 0x12) {
-      if (nt1) m2_gemv_small<false, 1, XF_BF16T, false, 1, 2>(a, p, nx, smem, gs, tag);
-      else m2_gemv_small<false, 2, XF_BF16T, false, 1, 2>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv_small<false, 1, XF_BF16T, false, 1, 2>(a, p, nx, smem, gs, tag);
+      else return m2_gemv_small<false, 2, XF_BF16T, false, 1, 2>(a, p, nx, smem, gs, tag);
     } else {                // 0x13
-      if (nt1) m2_gemv_small<false, 1, XF_BF16T, false, 1, 3>(a, p, nx, smem, gs, tag);
-      else m2_gemv_small<false, 2, XF_BF16T, false, 1, 3>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv_small<false, 1, XF_BF16T, false, 1, 3>(a, p, nx, smem, gs, tag);
+      else return m2_gemv_small<false, 2, XF_BF16T, false, 1, 3>(a, p, nx, smem, gs, tag);
     }
-    return;
   }
   const bool xres = norm && p.K <= 2048 && (p.K & 1023) == 0;
   if (dual) {               // NORM, f32 input
     if (xres) {
-      if (nt1) m2_gemv<true, 1, XF_F32T, true, true>(a, p, nx, smem, gs, tag);
-      else m2_gemv<true, 2, XF_F32T, true, true>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv<true, 1, XF_F32T, true, true>(a, p, nx, smem, gs, tag);
+      else return m2_gemv<true, 2, XF_F32T, true, true>(a, p, nx, smem, gs, tag);
     } else {
-      if (nt1) m2_gemv<true, 1, XF_F32T, true, false>(a, p, nx, smem, gs, tag);
-      else m2_gemv<true, 2, XF_F32T, true, false>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv<true, 1, XF_F32T, true, false>(a, p, nx, smem, gs, tag);
+      else return m2_gemv<true, 2, XF_F32T, true, false>(a, p, nx, smem, gs, tag);
     }
   } else if (norm) {
     if (xres) {
-      if (nt1) m2_gemv<false, 1, XF_BF16T, true, true>(a, p, nx, smem, gs, tag);
-      else m2_gemv<false, 2, XF_BF16T, true, true>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv<false, 1, XF_BF16T, true, true>(a, p, nx, smem, gs, tag);
+      else return m2_gemv<false, 2, XF_BF16T, true, true>(a, p, nx, smem, gs, tag);
     } else {
-      if (nt1) m2_gemv<false, 1, XF_BF16T, true, false>(a, p, nx, smem, gs, tag);
-      else m2_gemv<false, 2, XF_BF16T, true, false>(a, p, nx, smem, gs, tag);
+      if (nt1) return m2_gemv<false, 1, XF_BF16T, true, false>(a, p, nx, smem, gs, tag);
+      else return m2_gemv<false, 2, XF_BF16T, true, false>(a, p, nx, smem, gs, tag);
     }
   } else if (p.xf == XF_GATHER) {
-    if (nt1) m2_gemv<false, 1, XF_GATHER, false, false>(a, p, nx, smem, gs, tag);
-    else m2_gemv<false, 2, XF_GATHER, false, false>(a, p, nx, smem, gs, tag);
+    if (nt1) return m2_gemv<false, 1, XF_GATHER, false, false>(a, p, nx, smem, gs, tag);
+    else return m2_gemv<false, 2, XF_GATHER, false, false>(a, p, nx, smem, gs, tag);
   } else {
-    if (nt1) m2_gemv<false, 1, XF_BF16T, false, false>(a, p, nx, smem, gs, tag);
-    else m2_gemv<false, 2, XF_BF16T, false, false>(a, p, nx, smem, gs, tag);
+    if (nt1) return m2_gemv<false, 1, XF_BF16T, false, false>(a, p, nx, smem, gs, tag);
+    else return m2_gemv<false, 2, XF_BF16T, false, false>(a, p, nx, smem, gs, tag);
   }
 }
 
@@ -881,7 +891,8 @@ __device__ __forceinline__ void m2_gemv_dispatch(const M2Args& a, const M2Phase&
 // Input: tagged qkv rows; output: tagged attention rows.  The K/V rows of earlier positions were written by THIS
 // CTA (same item -> same CTA in every frame) or by the prefill kernels, so they need no tags.
 constexpr int M2_ATT_FAST_L = 16;
-__device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync& gs, const uint32_t tag) {
+__device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
+                                                   const uint32_t tag) {
   const bool cp = (p.flags & PF_CP) != 0;
   const bool prof_on = a.prof != nullptr;
   const int max_seq = cp ? a.cp_max_seq : a.max_seq;
@@ -1124,6 +1135,7 @@ __device__ __noinline__ void m2_attn(const M2Args& a, const M2Phase& p, unsigned
   m2_csync();
   m2_arrive(gs, p.flags);
   if (prof_on) prof2(a, 7);
+  return m2_pack(gs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1205,10 +1217,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega2_kernel(co
       const int nxi = p.next_gemv;
       const M2Phase* nx = (nxi >= 0 && (nxi > i || frame + 1 < a.n_frames)) ? &prog[nxi] : nullptr;
       switch (p.kind) {
-        case M2_GEMV: m2_gemv_dispatch(a, p, nx, work, gs, tag); break;
+        case M2_GEMV: m2_unpack(gs, m2_gemv_dispatch(a, p, nx, work, gs, tag)); break;
         case M2_ATTN:
           m2_prefetch(a, nx);
-          m2_attn(a, p, work, gs, tag);
+          m2_unpack(gs, m2_attn(a, p, work, gs, tag));
           break;
         case M2_PROLOGUE: {
           m2_wait(gs, p.flags);

@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_frames_mega3_kernel(cons
       } else {
         M2Sync gs{a.bar, a.err, st.epoch, gridDim.x, st.dead, st.arr, st.retries};
         switch (p.kind) {
-          case M2_ATTN: m2_attn(a, p, work, gs, tag); break;
+          case M2_ATTN: m2_unpack(gs, m2_attn(a, p, work, gs, tag)); break;
           case M2_PROLOGUE: {
             m2_wait(gs, p.flags);
             if (frame > 0 && a.do_sample) {
