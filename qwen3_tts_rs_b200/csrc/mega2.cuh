@@ -314,8 +314,17 @@ __device__ __forceinline__ void m2_tail(const M2Args& a, const M2Phase& p, const
   if (prof_on) m2_stamp(gs, 2);
   m2_csync();
   if (prof_on) prof2(a, 4);
+  // descriptor fields used below, read once (the slot stores are asm volatile with a memory clobber, so the compiler
+  // would re-read them from shared memory in every iteration)
+  const int epi = p.epi, yf = p.yf, ldy = p.ldy, pN = p.N;
+  u64* const Y64 = reinterpret_cast<u64*>(p.Y);
+  float* const Yf = p.Yf;
+  u64* const amax = p.amax;
+  const bf16* const bias = p.aux;
+  // idx = tid + it * 512 -> token idx >> 6: with one token tile (T <= 8) the second iteration has no valid output
+  constexpr int N_IT = NT == 1 ? 1 : MEGA_MAX_OUT;
 #pragma unroll
-  for (int it = 0; it < MEGA_MAX_OUT; ++it) {
+  for (int it = 0; it < N_IT; ++it) {
     const int idx = tid + it * MEGA_THREADS;
     const int t = idx >> 6, rem = idx & 63;
     const int n = r0 + rem, nt = t >> 3, col = t & 7;
@@ -331,34 +340,34 @@ __device__ __forceinline__ void m2_tail(const M2Args& a, const M2Phase& p, const
         if (DUAL) v1 += rb[8 * red_cs + w * red_r];
       }
       const float v = rbf(v0);
-      switch (p.epi) {
+      switch (epi) {
         case EPI_STORE: outv = v; break;
-        case EPI_BIAS: outv = rbf(v + bf2f(p.aux[n])); break;
+        case EPI_BIAS: outv = rbf(v + bf2f(bias[n])); break;
         case EPI_RESIDUAL: outv = rbf(rres[it] + v); break;
         case EPI_O_H1: outv = rres[it] + v; break;       // x + attn_out, un-rounded (fused_residual_rmsnorm.cu:60-65)
         case EPI_SWIGLU: outv = rbf(rbf(silu_f(v)) * rbf(v1)); break;
         case EPI_LOGITS: {
-          if (p.Yf != nullptr) p.Yf[(size_t)t * p.N + n] = v;
+          if (Yf != nullptr) Yf[(size_t)t * pN + n] = v;
           key = argmax_key(v, n);
         } break;
         default: break;
       }
     }
-    if (p.yf == XF_BF16T) {
+    if (yf == XF_BF16T) {
       const float other = __shfl_xor_sync(0xffffffffu, outv, 1);
       if (valid && !(lane & 1))
-        st_slot(reinterpret_cast<u64*>(p.Y) + (((size_t)t * p.ldy + n) >> 1), pack2(outv, other), tag);
-    } else if (p.yf == XF_F32T) {
-      if (valid) st_slot(reinterpret_cast<u64*>(p.Y) + (size_t)t * p.ldy + n, __float_as_uint(outv), tag);
+        st_slot(Y64 + (((size_t)t * ldy + n) >> 1), pack2(outv, other), tag);
+    } else if (yf == XF_F32T) {
+      if (valid) st_slot(Y64 + (size_t)t * ldy + n, __float_as_uint(outv), tag);
     }
-    if (p.epi == EPI_LOGITS && p.amax != nullptr) {
+    if (epi == EPI_LOGITS && amax != nullptr) {
       // a warp covers 32 consecutive rows of ONE token: one atomic per warp instead of 32 on the same address
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         const u64 other = __shfl_xor_sync(0xffffffffu, key, o);
         key = other > key ? other : key;
       }
-      if (lane == 0 && key != 0ull) atomicMax(p.amax + t, key);
+      if (lane == 0 && key != 0ull) atomicMax(amax + t, key);
     }
   }
   m2_csync();
