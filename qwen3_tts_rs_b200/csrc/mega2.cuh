@@ -282,19 +282,24 @@ __device__ __forceinline__ void m2_token_rows(const M2Args& a, const M2Phase& p,
 
 // residual inputs of the epilogue: rows owned by this CTA, written by this CTA two or three phases ago.
 // Combine mapping: output idx = tid + it*512 -> token t = idx >> 6, CTA-local row = idx & 63.
+template <int NT>
 __device__ __forceinline__ void m2_load_residual(const M2Phase& p, int r0, int r1, float (&rres)[MEGA_MAX_OUT]) {
   const int tid = threadIdx.x;
+  const int epi = p.epi, T = p.T, rf = p.rf, ldr = p.ldr;
+  const u64* const R64 = reinterpret_cast<const u64*>(p.R);
+  const bool has_r = epi == EPI_RESIDUAL || epi == EPI_O_H1;
 #pragma unroll
   for (int it = 0; it < MEGA_MAX_OUT; ++it) {
     rres[it] = 0.f;
+    if (NT == 1 && it >= 1) continue;          // one token tile: the second output iteration does not exist (m2_tail)
     const int idx = tid + it * MEGA_THREADS;
     const int t = idx >> 6, n = r0 + (idx & 63);
-    if ((p.epi == EPI_RESIDUAL || p.epi == EPI_O_H1) && t < p.T && n < r1) {
-      if (p.rf == XF_F32T) {
-        const u64 s = ld_slot(reinterpret_cast<const u64*>(p.R) + (size_t)t * p.ldr + n);
+    if (has_r && t < T && n < r1) {
+      if (rf == XF_F32T) {
+        const u64 s = ld_slot(R64 + (size_t)t * ldr + n);
         rres[it] = rbf(__uint_as_float(slot_val(s)));            // h1 as the reference stores it: bf16(x + attn)
       } else {
-        const u64 s = ld_slot(reinterpret_cast<const u64*>(p.R) + (((size_t)t * p.ldr + n) >> 1));
+        const u64 s = ld_slot(R64 + (((size_t)t * ldr + n) >> 1));
         rres[it] = (n & 1) ? bf_hi(slot_val(s)) : bf_lo(slot_val(s));
       }
     }
@@ -495,7 +500,7 @@ __device__ __noinline__ unsigned long long m2_gemv(const M2Args& a, const M2Phas
         if (c < n_chunks) wnr[c][u] = *reinterpret_cast<const uint4*>(p.aux + koff0 + (c * JU + u) * 512);
       }
   }
-  m2_load_residual(p, r0, r1, rres);
+  m2_load_residual<NT>(p, r0, r1, rres);
   m2_wait(gs, p.flags);
   if (prof_on) prof2(a, 2);
   if (prof_on) m2_stamp(gs, 0);
@@ -758,7 +763,7 @@ __device__ __noinline__ unsigned long long m2_gemv_small(const M2Args& a, const 
 #pragma unroll
       for (int u = 0; u < JU; ++u) wn[c][u] = *reinterpret_cast<const uint4*>(p.aux + koff0 + (c * JU + u) * 512);
   }
-  m2_load_residual(p, r0, r1, rres);
+  m2_load_residual<NT>(p, r0, r1, rres);
   m2_wait(gs, p.flags);
   if (prof_on) prof2(a, 2);
   if (prof_on) m2_stamp(gs, 0);

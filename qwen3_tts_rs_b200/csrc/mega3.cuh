@@ -113,7 +113,7 @@ __device__ __noinline__ M3State m3_gemv(M3Shared& sh, const M2Phase& p, unsigned
   const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
   const int koff0 = warp * 32 + 8 * tg;              // element offset of this lane inside a chunk's 512 columns
   float rres[MEGA_MAX_OUT];
-  m2_load_residual(p, r0, r1, rres);
+  m2_load_residual<NT>(p, r0, r1, rres);
   uint4 wn[KCH];
   if constexpr (NORM) {
 #pragma unroll
