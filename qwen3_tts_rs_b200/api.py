@@ -80,6 +80,29 @@ class AudioBuffer:
     def duration(self) -> float:
         return len(self) / self.sample_rate
 
+    def is_empty(self) -> bool:
+        return len(self) == 0
+
+    def save(self, path: str) -> None:
+        """AudioBuffer::save (io.rs:71-73): PCM16 mono WAV."""
+        from . import formats
+        formats.save_wav(path, self.samples, self.sample_rate)
+
+    @classmethod
+    def load(cls, path: str) -> "AudioBuffer":
+        """AudioBuffer::load (io.rs:76-78)."""
+        from . import formats
+        samples, rate = formats.load_wav(path)
+        return cls(samples, rate)
+
+    def normalize(self) -> None:
+        from . import formats
+        self.samples = formats.normalize(self.samples)
+
+    def normalize_db(self, target_db: float) -> None:
+        from . import formats
+        self.samples = formats.normalize_db(self.samples, target_db)
+
 
 def codes_to_tensor(codes: Sequence[Sequence[int]]) -> np.ndarray:
     """src/lib.rs:1417-1431: [n_frames][16] u32 -> i64 [1,16,T], data[q*T + f] = codes[f][q]."""
@@ -345,6 +368,7 @@ class Qwen3TTS:
     def __init__(self, model: Model):
         self.model = model
         self.spec = model.spec
+        self.model_type: Optional[str] = None
 
     @classmethod
     def from_weights(cls, spec: ModelSpec, talker_weights: Dict[str, torch.Tensor],
@@ -355,6 +379,26 @@ class Qwen3TTS:
             m.load(vocoder_weights)
         m.finalize()
         return cls(m)
+
+    @classmethod
+    def from_pretrained(cls, model_id: str, device: int = 0) -> "Qwen3TTS":
+        """Qwen3TTS::from_pretrained (lib.rs:183-262) for the decode path: a local checkpoint directory with
+        config.json (optional), model.safetensors and speech_tokenizer/model.safetensors.  Tokenizer loading and hub
+        download are outside the hot path (callers pass token ids).  The variant detected from config.json is kept
+        in `model_type` (None when the dimensions came from weight inspection, lib.rs:383-386)."""
+        from . import formats
+        ck = formats.load_checkpoint(model_id)
+        tts = cls.from_weights(ck.spec, ck.talker_weights, ck.vocoder_weights, device)
+        tts.model_type = ck.config.model_type if ck.config is not None else None
+        return tts
+
+    def supports_preset_speakers(self) -> bool:
+        """lib.rs:393-404: CustomVoice only; permissive when the variant is unknown."""
+        return self.model_type in (None, "custom_voice")
+
+    def supports_voice_design(self) -> bool:
+        """lib.rs:406-411: VoiceDesign only (an unknown variant is NOT accepted here, unlike the preset speakers)."""
+        return self.model_type == "voice_design"
 
     # -- prompt assembly (host logic only: id lists; embedding math runs on the device) -----------------
     def custom_voice_prompt(self, text_ids: Sequence[int], speaker: str, language: str):
