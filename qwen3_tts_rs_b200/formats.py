@@ -569,3 +569,39 @@ def export_checkpoint(model_dir: str, spec: ModelSpec, talker_weights: Dict[str,
             f.write(vocoder_config_json(spec.vocoder))
     save_safetensors(talker_weights, os.path.join(model_dir, "model.safetensors"), {"format": "pt"})
     save_safetensors(vocoder_weights, os.path.join(model_dir, "speech_tokenizer", "model.safetensors"), {"format": "pt"})
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the file set `generate_audio` leaves in --output-dir (src/bin/generate_audio.rs:686-741)
+# ------------------------------------------------------------------------------------------------------------
+
+
+def max_frames_from_args(frames: int, duration: Optional[float]) -> int:
+    """generate_audio.rs:137-144: `--duration` seconds override `--frames` at 12.5 frames per second, truncated."""
+    return int(duration * 12.5) if duration is not None else frames
+
+
+def write_generation_outputs(output_dir: str, seed: int, codes: Sequence[Sequence[int]], audio: np.ndarray,
+                             text: str, input_ids: Sequence[int], temperature: float, top_k: int, top_p: float,
+                             wav_path: Optional[str] = None) -> Dict[str, str]:
+    """codes_seed{S}_frames{N}.bin, audio_seed{S}_frames{N}.wav / .bin and metadata_seed{S}_frames{N}.json with the
+    `GenerationMetadata` fields (generate_audio.rs:123-135), N = frames actually generated.  -> the paths."""
+    n = len(codes)
+    audio = np.asarray(audio, dtype=np.float32).reshape(-1)
+    os.makedirs(output_dir, exist_ok=True)
+    stem = f"seed{seed}_frames{n}"
+    paths = {"codes": os.path.join(output_dir, f"codes_{stem}.bin"),
+             "wav": wav_path or os.path.join(output_dir, f"audio_{stem}.wav"),
+             "audio": os.path.join(output_dir, f"audio_{stem}.bin"),
+             "metadata": os.path.join(output_dir, f"metadata_{stem}.json")}
+    if wav_path and os.path.dirname(wav_path):
+        os.makedirs(os.path.dirname(wav_path), exist_ok=True)
+    save_codes_binary(codes, paths["codes"])
+    save_wav(paths["wav"], audio, 24000)
+    save_audio_binary(audio, paths["audio"])
+    meta = {"text": text, "seed": int(seed), "num_frames": n, "temperature": float(temperature), "top_k": int(top_k),
+            "top_p": float(top_p), "input_ids": [int(i) for i in input_ids], "codes_shape": [1, 16, n],
+            "audio_samples": int(audio.size), "sample_rate": 24000}
+    with open(paths["metadata"], "w", encoding="utf-8") as f:
+        json.dump(meta, f, indent=2)
+    return paths

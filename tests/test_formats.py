@@ -349,3 +349,53 @@ def test_load_checkpoint_lookup_rules_and_errors(tiny_checkpoint, tmp_path):
     (m / "config.json").write_text(F.config_json_for_spec(spec))
     with pytest.raises(KeyError, match="Missing weight: talker.codec_head.weight"):
         F.load_checkpoint(str(m))
+
+
+def test_formats_match_the_c_oracle(tmp_path):
+    """Product-side byte formats against oracle/c's plain-C restatement (codes dump, PCM16 rule) on seeded inputs."""
+    import ctypes as C
+    from oracle import build_ref
+    lib = C.CDLL(build_ref.build_c())
+    rng = np.random.default_rng(7)
+    codes = rng.integers(0, 3072, size=(37, 16), dtype=np.uint32)
+    want = np.zeros(37 * 16 * 8, dtype=np.uint8)
+    lib.q3o_codes_dump(codes.ctypes.data_as(C.c_void_p), 37, want.ctypes.data_as(C.c_void_p))
+    p = str(tmp_path / "c.bin")
+    F.save_codes_binary(codes.tolist(), p)
+    assert open(p, "rb").read() == want.tobytes()
+    x = np.concatenate([rng.uniform(-1.5, 1.5, 100000), [1.0, -1.0, 0.0, -0.0, 1e-30]]).astype(np.float32)
+    pcm = np.zeros(x.size, dtype=np.int16)
+    lib.q3o_pcm16(x.ctypes.data_as(C.c_void_p), x.size, pcm.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(F.pcm_f32_to_i16(x), pcm)
+
+
+def test_generate_audio_file_set(tmp_path):
+    """generate_audio.rs:137-144 (frames from --duration) and :686-741 (file names, metadata fields)."""
+    assert F.max_frames_from_args(2048, None) == 2048 and F.max_frames_from_args(2048, 10.0) == 125
+    assert F.max_frames_from_args(7, 0.1) == 1                     # (0.1 * 12.5) as usize
+    codes = [[q for q in range(16)] for _ in range(3)]
+    audio = np.zeros(3 * 1920, np.float32)
+    paths = F.write_generation_outputs(str(tmp_path / "o"), 42, codes, audio, "Hello", [9, 8], 0.7, 50, 0.9)
+    assert sorted(os.listdir(tmp_path / "o")) == ["audio_seed42_frames3.bin", "audio_seed42_frames3.wav",
+                                                  "codes_seed42_frames3.bin", "metadata_seed42_frames3.json"]
+    meta = json.load(open(paths["metadata"]))
+    assert list(meta) == ["text", "seed", "num_frames", "temperature", "top_k", "top_p", "input_ids", "codes_shape",
+                          "audio_samples", "sample_rate"]
+    assert meta["codes_shape"] == [1, 16, 3] and meta["audio_samples"] == 5760 and meta["sample_rate"] == 24000
+    rep = F.compare_with_reference(str(tmp_path / "o"), 42, 3, codes, audio)   # a run compares clean against itself
+    assert rep.codes_match and rep.max_diff == 0.0
+    paths = F.write_generation_outputs(str(tmp_path / "o"), 1, codes, audio, "", [], 0.7, 50, 0.9,
+                                       wav_path=str(tmp_path / "elsewhere" / "x.wav"))
+    assert os.path.exists(tmp_path / "elsewhere" / "x.wav") and not os.path.exists(tmp_path / "o" / "audio_seed1_frames3.wav")
+
+
+def test_generate_audio_tool_exports_a_loadable_checkpoint(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = str(tmp_path / "synth")
+    subprocess.run([sys.executable, os.path.join(root, "tools", "generate_audio.py"), "--export-synthetic", "tiny_proj",
+                    "--model-dir", d, "--model-type", "voice_design"], check=True, capture_output=True)
+    ck = F.load_checkpoint(d)
+    assert ck.config.model_type == "voice_design" and ck.spec.has_cp_proj and ck.spec.vocoder == S.TINY_VOCODER
+    assert "talker.code_predictor.small_to_mtp_projection.bias" in ck.talker_weights
