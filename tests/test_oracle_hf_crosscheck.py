@@ -1,0 +1,130 @@
+"""Second witness for the oracle's transformer stack (SURVEY.md §8(c) "independent cross-check available offline").
+
+`transformers` 5.5 ships the Qwen3 dense decoder (`models/qwen3/modeling_qwen3.py`): RMSNorm -> q/k/v with per-head
+q_norm / k_norm before RoPE -> rotate-half RoPE -> GQA attention -> o_proj -> residual -> RMSNorm -> SwiGLU -> residual.
+That is the architecture the reference's talker and code predictor implement (transformer.rs:247-467), written by
+different people.  Loading the SAME synthetic weights into it and into the oracle (F32 mode) must give the same
+hidden states and logits up to F32 summation order; a structural mistake in the oracle (norm placement, RoPE
+pairing, GQA head mapping, scale, mask, cache offsets) would show up as an O(1) difference.
+
+This pins the op ORDER of the oracle, not candle's bf16 rounding points (nothing offline can: SURVEY §8(c)).
+Where HF and the Rust reference differ, the Rust reference wins; for this stack they do not differ.
+"""
+import pytest
+import torch
+
+from qwen3_tts_rs_b200 import spec as S, weights as W
+from oracle import model as OM
+
+HF = pytest.importorskip("transformers.models.qwen3.modeling_qwen3")
+
+
+def _hf_stack(spec, w, prefix, hidden, inter, layers, heads, kv_heads, vocab, embed, head):
+    cfg = HF.Qwen3Config(vocab_size=vocab, hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
+                         num_attention_heads=heads, num_key_value_heads=kv_heads, head_dim=spec.head_dim,
+                         rms_norm_eps=spec.rms_eps, rope_theta=spec.rope_theta, attention_bias=False,
+                         max_position_embeddings=4096, tie_word_embeddings=False, use_sliding_window=False,
+                         attn_implementation="eager")
+    cfg.rope_parameters = {"rope_type": "default", "rope_theta": spec.rope_theta}
+    m = HF.Qwen3ForCausalLM(cfg).eval().to(torch.float32)
+    sd = {"model." + k[len(prefix) + 1:]: v for k, v in w.items()
+          if k.startswith(prefix + ".layers.") or k == prefix + ".norm.weight"}
+    sd["model.embed_tokens.weight"] = embed
+    sd["lm_head.weight"] = head
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+@pytest.mark.parametrize("spec", [S.SPEC_TINY, S.SPEC_TINY_PROJ], ids=lambda s: s.name)
+def test_talker_prefill_and_steps_match_hf_qwen3(spec):
+    """run_prefill_layers (talker.rs:823-841) and generate_step_with_embed (talker.rs:716-736), F32."""
+    w = W.make_talker_weights(spec, dtype=torch.float32)
+    m = _hf_stack(spec, w, "talker.model", spec.hidden, spec.inter, spec.layers, spec.heads, spec.kv_heads,
+                  spec.codec_vocab, w["talker.model.codec_embedding.weight"], w["talker.codec_head.weight"])
+    g = torch.Generator().manual_seed(5)
+    emb = 0.05 * torch.randn(1, 12, spec.hidden, generator=g)
+    tk = OM.Talker(spec, w, OM.F32P)
+    caches = tk.new_kv_caches()
+    with torch.no_grad():
+        out = m(inputs_embeds=emb[:, :9], use_cache=True)
+        hs = m.model(inputs_embeds=emb[:, :9]).last_hidden_state
+    h, lg = tk.run_prefill_layers(emb[:, :9], caches)
+    scale = float(hs.abs().max())
+    assert float((h - hs).abs().max()) <= 2e-5 * scale
+    assert float((lg[0, 0] - out.logits[0, -1]).abs().max()) <= 2e-5 * float(out.logits.abs().max())
+    past = out.past_key_values
+    for pos in range(9, 12):                                      # decode steps over the KV cache, offset = position
+        with torch.no_grad():
+            o = m(inputs_embeds=emb[:, pos:pos + 1], past_key_values=past, use_cache=True,
+                  position_ids=torch.tensor([[pos]]), output_hidden_states=True)
+        past = o.past_key_values
+        h1, l1 = tk.generate_step_with_embed(emb[:, pos:pos + 1], caches, pos)
+        assert float((l1[0, 0] - o.logits[0, -1]).abs().max()) <= 2e-5 * float(o.logits.abs().max()), pos
+        assert int(torch.argmax(l1)) == int(torch.argmax(o.logits[0, -1]))
+
+
+def test_code_predictor_passes_match_hf_qwen3():
+    """generate_acoustic_codes (code_predictor.rs:320-416): the two-token causal first pass at offset 0, then 14
+    single-token passes at offsets 2..15 over the same caches, greedy arg-max per head -- driven here through HF's
+    Qwen3 stack with the oracle's embeddings and heads, and compared code for code and logit for logit."""
+    spec = S.SPEC_TINY_PROJ                                       # has small_to_mtp_projection, like the 1.7B
+    w = W.make_talker_weights(spec, dtype=torch.float32)
+    cp = OM.CodePredictor(spec, w, OM.F32P)
+    pre = "talker.code_predictor"
+    m = _hf_stack(spec, w, pre + ".model", spec.cp_hidden, spec.cp_inter, spec.cp_layers, spec.cp_heads, spec.cp_kv_heads,
+                  spec.cp_vocab, torch.zeros(spec.cp_vocab, spec.cp_hidden), w[pre + ".lm_head.0.weight"])
+    g = torch.Generator().manual_seed(11)
+    talker_hidden = torch.randn(1, 1, spec.hidden, generator=g)
+    sem = w["talker.model.codec_embedding.weight"][123][None, None]
+    codes, logits = cp.generate_acoustic_codes(talker_hidden, sem, cp.new_kv_caches(), return_logits=True)
+    pw, pb = w[pre + ".small_to_mtp_projection.weight"], w[pre + ".small_to_mtp_projection.bias"]
+    proj = lambda x: x @ pw.T + pb
+    with torch.no_grad():
+        o = m.model(inputs_embeds=proj(torch.cat([talker_hidden, sem], 1)), use_cache=True)
+        past = o.past_key_values
+        hf_codes, h = [], o.last_hidden_state[:, 1:2]
+        for grp in range(15):
+            lg = h[0, 0] @ w[f"{pre}.lm_head.{grp}.weight"].T
+            assert float((lg - logits[grp]).abs().max()) <= 5e-5 * float(lg.abs().max()), grp
+            hf_codes.append(int(torch.argmax(lg)))
+            if grp == 14:
+                break
+            e = w[f"{pre}.model.codec_embedding.{grp}.weight"][hf_codes[-1]][None, None]
+            o = m.model(inputs_embeds=proj(e), past_key_values=past, use_cache=True,
+                        position_ids=torch.tensor([[grp + 2]]))
+            past, h = o.past_key_values, o.last_hidden_state
+    assert hf_codes == codes
+
+
+def test_vocoder_pre_transformer_matches_hf_code2wav():
+    """decoder_12hz.rs:536-699 (8-layer pre-transformer: RMSNorm eps 1e-5, rotate-half RoPE, scale after QK^T, full causal
+    mask, layer-scale then residual) against transformers' `Qwen3OmniMoeCode2WavTransformerModel` on the same weights.
+    HF applies a 72-position sliding window; the Rust reference attends to the full causal prefix (decoder_12hz.rs:
+    557-564, 642) and wins -- so HF is given a window wider than the sequence, and the layer scales are set to O(1) so that a
+    mistake inside a branch is not hidden behind the 0.01 factor."""
+    mm = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    cc = pytest.importorskip("transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe")
+    from oracle import vocoder as OV
+    v = S.TINY_VOCODER
+    w = dict(W.make_vocoder_weights(v))
+    g = torch.Generator().manual_seed(2)
+    for k in list(w):
+        if k.endswith("_layer_scale.scale"):
+            w[k] = 0.5 + torch.rand(w[k].shape, generator=g)
+    cfg = cc.Qwen3OmniMoeCode2WavConfig(
+        hidden_size=v.hidden_size, num_attention_heads=v.num_heads, num_key_value_heads=v.num_heads,
+        intermediate_size=v.intermediate_size, num_hidden_layers=v.num_layers, rms_norm_eps=v.rms_norm_eps,
+        sliding_window=4096, rope_parameters={"rope_type": "default", "rope_theta": v.rope_theta})
+    cfg.head_dim = v.head_dim
+    cfg._attn_implementation = "eager"
+    m = mm.Qwen3OmniMoeCode2WavTransformerModel(cfg).eval()
+    pre = "decoder.pre_transformer."
+    m.load_state_dict({k[len(pre):]: t for k, t in w.items() if k.startswith(pre + "layers.") or k == pre + "norm.weight"},
+                      strict=True)
+    voc = OV.Vocoder(v, w)
+    for t in (1, 7, 100):
+        x = torch.randn(2, t, v.hidden_size, generator=g)
+        with torch.no_grad():
+            y = m(inputs_embeds=x).last_hidden_state
+        mine = voc._rms(voc._transformer(x), w[pre + "norm.weight"])
+        assert float((y - mine).abs().max()) <= 2e-5 * float(y.abs().max()), t
