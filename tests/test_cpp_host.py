@@ -1,0 +1,187 @@
+"""The C++ host mirror (include/q3tts.hpp) against the Python mirror (api.py / formats.py): same prompts, same bytes
+on disk, same config / safetensors parsing; and -- on the GPU -- the same codes and PCM for the same checkpoint, seed
+and prompt, because both are thin layers over one C ABI.  The reference is compiled code (Rust); this is the
+compiled-language caller a maintainer would model the Rust shim on."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from qwen3_tts_rs_b200 import api, formats as F, spec as S, weights as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "qwen3_tts_rs_b200")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory, lib):
+    out = str(tmp_path_factory.mktemp("cpp") / "host_mirror_check")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "host_mirror_check.cpp"), "-o", out,
+           "-L", LIBDIR, "-lq3tts_b200", f"-Wl,-rpath,{LIBDIR}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return out
+
+
+def run(exe, *args, ok=True):
+    r = subprocess.run([exe, *map(str, args)], capture_output=True, text=True, timeout=900)
+    if ok:
+        assert r.returncode == 0, (r.returncode, r.stderr[-2000:])
+    return r
+
+
+def _lines(r):
+    return {ln.split(" ", 1)[0]: ln.split(" ", 1)[1] if " " in ln else "" for ln in r.stdout.strip().splitlines()}
+
+
+@pytest.mark.parametrize("spec", [S.SPEC_1_7B, S.SPEC_TINY], ids=lambda s: s.name)
+def test_prompts_match_the_python_mirror(exe, spec):
+    """prefill_custom_voice / prefill_voice_design id layouts (talker.rs:451-491, 585-627)."""
+    t = api.Qwen3TTS.__new__(api.Qwen3TTS)
+    t.spec = spec
+    for ids in ([], [7], [11, 12, 13, 14]):
+        inst = [101, 102, 103]
+        out = _lines(run(exe, "prompts", spec.text_vocab, ",".join(map(str, ids)), ",".join(map(str, inst))))
+        cv = t.custom_voice_prompt(ids, "ryan", "english")
+        vd = t.voice_design_prompt(ids, inst, "japanese")
+        assert [int(x) for x in out["cv_text"].split()] == cv[0] and [int(x) for x in out["cv_codec"].split()] == cv[1]
+        assert [int(x) for x in out["vd_text"].split()] == vd[0] and [int(x) for x in out["vd_codec"].split()] == vd[1]
+        assert out["speaker_unknown"] == "0"
+        assert len(cv[0]) == (10 if ids else 9)                    # talker.rs:437-449
+
+
+def test_formats_are_byte_identical(exe, tmp_path):
+    d = str(tmp_path)
+    codes = [[(f * 131 + q * 17) % 3072 for q in range(16)] for f in range(5)]
+    i = np.arange(3000, dtype=np.float32)
+    audio = (np.float32(1.3) * np.sin(np.float32(0.01) * i).astype(np.float32)) * np.where(np.arange(3000) % 7, 1, -1).astype(np.float32)
+    F.save_codes_binary(codes, d + "/py_codes.bin")
+    F.save_wav(d + "/py.wav", audio, 24000)
+    F.save_codes_binary(codes, d + "/codes_seed7_frames5.bin")
+    F.save_audio_binary(audio, d + "/audio_seed7_frames5.bin")
+    out = _lines(run(exe, "formats", d))
+    assert open(d + "/cpp_codes.bin", "rb").read() == open(d + "/py_codes.bin", "rb").read()
+    # the C++ program computed its own sine: compare its audio dump / WAV with Python's conversion of THAT dump
+    cpp_audio = F.load_audio_binary(d + "/cpp_audio.bin")
+    assert np.abs(cpp_audio - audio).max() < 1e-5
+    F.save_wav(d + "/py_from_cpp.wav", cpp_audio, 24000)
+    assert open(d + "/cpp.wav", "rb").read() == open(d + "/py_from_cpp.wav", "rb").read()
+    assert [int(x) for x in out["tensor"].split()] == api.codes_to_tensor(codes).reshape(-1).tolist()
+    assert out["py_codes_equal"] == "1"
+    w, rate = F.load_wav(d + "/py.wav")
+    h = 1469598103934665603
+    for b in w.astype("<f4").tobytes():
+        h = ((h ^ b) * 1099511628211) & (2 ** 64 - 1)
+    assert out["py_wav"].split() == ["24000", "3000", f"{h:016x}"]
+    # compare_with_reference after the program perturbed one code and one sample of ITS data
+    bad = [list(fr) for fr in codes]
+    bad[2][3] += 1
+    a2 = cpp_audio.copy()
+    a2[10] += np.float32(0.5)
+    rep = F.compare_with_reference(d, 7, 5, bad, a2)
+    c = out["compare"].split()
+    assert c[:5] == ["1", "0", "1", "80", "3000"] and rep.n_code_diffs == 1 and not rep.codes_match
+    assert abs(float(c[5]) - rep.max_diff) < 1e-6 and abs(float(c[6]) - rep.mean_diff) < 1e-9 and abs(float(c[7]) - rep.rmse) < 1e-9
+    assert np.allclose([float(x) for x in out["normalize"].split()], [1.0, -0.5, 0.2], atol=1e-6)   # io.rs:200-207
+
+
+def test_config_parsing_matches(exe, tmp_path):
+    p = tmp_path / "config.json"
+    cases = [F.config_json_for_spec(S.SPEC_1_7B, "voice_design"), F.config_json_for_spec(S.SPEC_0_6B, "base"), "{}",
+             json.dumps({"tts_model_type": "custom_voice", "tts_model_size": "1b7", "speaker_encoder_config": {"enc_dim": 2048},
+                         "talker_config": {"hidden_size": 2048, "rope_theta": 1e6, "rms_norm_eps": 1e-06, "num_hidden_layers": "x",
+                                           "rope_scaling": {"mrope_section": [24, 20, 20], "interleaved": True},
+                                           "code_predictor_config": {"vocab_size": 2048, "note": "café \"q\""}}})]
+    for text in cases:
+        p.write_text(text)
+        c = F.ParsedModelConfig.from_file(str(p))
+        out = _lines(run(exe, "config", p))
+        assert out["label"] == c.label()
+        t = out["talker"].split()
+        assert [int(x) for x in t[:9]] == [c.talker_hidden_size, c.talker_intermediate_size, c.talker_num_hidden_layers,
+                                           c.talker_num_attention_heads, c.talker_num_key_value_heads, c.talker_head_dim,
+                                           c.talker_vocab_size, c.talker_text_vocab_size, c.talker_text_hidden_size]
+        assert float(t[9]) == c.talker_rms_norm_eps and float(t[10]) == c.talker_rope_theta and int(t[11]) == c.talker_max_position_embeddings
+        q = out["cp"].split()
+        assert [int(x) for x in q[:8]] == [c.cp_hidden_size, c.cp_intermediate_size, c.cp_num_hidden_layers, c.cp_num_attention_heads,
+                                           c.cp_num_key_value_heads, c.cp_head_dim, c.cp_vocab_size, c.cp_num_code_groups]
+        assert out["mrope"] == ("none" if c.mrope_section is None else " ".join(map(str, c.mrope_section)))
+        assert int(out["speaker_enc_dim"]) == (-1 if c.speaker_enc_dim is None else c.speaker_enc_dim)
+    p.write_text("{ broken")
+    r = run(exe, "config", p, ok=False)
+    assert r.returncode == 10 + 1 and "Failed to parse config" in r.stderr
+
+
+def test_safetensors_mapping_matches(exe, tmp_path):
+    st = pytest.importorskip("safetensors.torch")
+    g = torch.Generator().manual_seed(9)
+    ts = {"talker.model.norm.weight": torch.randn(64, generator=g).to(torch.bfloat16),
+          "decoder.pre_conv.conv.weight": torch.randn(8, 4, 3, generator=g),
+          "half": torch.randn(5, generator=g).to(torch.float16), "ids": torch.arange(12).reshape(3, 4)}
+    for writer, name in ((lambda t, p: F.save_safetensors(t, p, {"format": "pt"}), "ours"), (st.save_file, "theirs")):
+        p = str(tmp_path / f"{name}.safetensors")
+        writer(ts, p)
+        got = {}
+        for ln in run(exe, "safetensors", p).stdout.strip().splitlines():
+            n, dt, shape, h = ln.split()
+            got[n] = (dt, shape, h)
+        assert set(got) == set(ts)
+        for k, v in ts.items():
+            h = 1469598103934665603
+            for b in v.contiguous().reshape(-1).view(torch.uint8).numpy().tobytes():
+                h = ((h ^ b) * 1099511628211) & (2 ** 64 - 1)
+            assert got[k] == (F._ST_NAMES[v.dtype], "[" + ",".join(map(str, v.shape)) + "]", f"{h:016x}"), k
+    p = str(tmp_path / "bad.safetensors")
+    raw = open(str(tmp_path / "ours.safetensors"), "rb").read()
+    open(p, "wb").write(raw[:-4])
+    assert run(exe, "safetensors", p, ok=False).returncode == 10 + 1
+
+
+def test_from_pretrained_fails_loudly_without_a_gpu(exe, tmp_path):
+    """No CPU fallback behind the C++ mirror either: the reference's error texts for missing files, and Q3_ERR_CUDA from
+    q3_model_create when the files are there but no sm_100 device is."""
+    r = run(exe, "generate", tmp_path / "nope", "1,2,3", 42, 4, tmp_path, ok=False)
+    assert r.returncode == 10 + 1 and "Model weights not found at" in r.stderr and "Please download the model first." in r.stderr
+    d = str(tmp_path / "tiny")
+    spec = S.SPEC_TINY
+    F.export_checkpoint(d, spec, W.make_talker_weights(spec), W.make_vocoder_weights(spec.vocoder))
+    os.rename(d + "/speech_tokenizer", d + "/st_moved")
+    r = run(exe, "generate", d, "1,2,3", 42, 4, tmp_path, ok=False)
+    assert r.returncode == 10 + 1 and "Speech tokenizer weights not found" in r.stderr
+    os.rename(d + "/st_moved", d + "/speech_tokenizer")
+    if not torch.cuda.is_available():
+        r = run(exe, "generate", d, "1,2,3", 42, 4, tmp_path, ok=False)
+        assert r.returncode == 10 + 2, (r.returncode, r.stderr)      # Q3_ERR_CUDA
+
+
+@pytest.mark.gpu
+def test_cpp_and_python_mirrors_generate_identical_output(exe, tmp_path):
+    spec = S.SPEC_TINY_PROJ
+    tw, vw = W.make_talker_weights(spec), W.make_vocoder_weights(spec.vocoder)
+    d = str(tmp_path / "ckpt")
+    F.export_checkpoint(d, spec, tw, vw, "custom_voice")
+    ids = W.synthetic_prompt(2, spec)
+    out_dir = str(tmp_path / "out")
+    os.makedirs(out_dir)
+    r = run(exe, "generate", d, ",".join(map(str, ids)), 42, 9, out_dir)
+    info = dict(zip(r.stdout.split()[::2], r.stdout.split()[1::2]))
+    tts = api.Qwen3TTS.from_pretrained(d)
+    opts = api.SynthesisOptions(max_length=9, seed=42)
+    codes = tts.generate_codes([ids], options=opts, seeds=[42])[0]
+    audio = tts.synthesize_with_voice([ids], options=opts, seeds=[42])[0]
+    assert int(info["frames"]) == len(codes) > 0 and int(info["samples"]) == len(audio)
+    assert info["generate_codes_equal"] == "1" and info["model_type"] == "1"
+    assert float(info["decode_codes_maxdiff"]) <= 1e-5            # q3_vocoder_decode vs q3_vocode_session on the same codes
+    assert int(info["launches"]) > 0
+    rep = F.compare_with_reference(out_dir, 42, len(codes), codes, audio.samples)
+    assert rep.codes_match and rep.audio_found and rep.max_diff == 0.0 and rep.n_audio_compared == len(audio)
+    # streaming through the C++ mirror: every frame arrives, in chunks of 3 (lib.rs:1650-1759)
+    assert int(info["stream_frames"]) == len(codes) and int(info["streamed_samples"]) == len(codes) * 1920
+    assert int(info["chunks"]) == -(-len(codes) // 3)
+    back = api.AudioBuffer.load(out_dir + "/audio.wav")
+    assert len(back) == len(audio) and np.abs(back.samples - audio.samples).max() <= 2.0 / 32768 + 1e-7
