@@ -139,6 +139,12 @@ q3_status q3_get_codes(q3_session* s, int32_t max_frames, uint32_t* codes, int32
  * codes: u32 [batch][chunk_frames][16]; pcm: f32 [batch][chunk_frames*1920]; n_frames[batch];
  * *done != 0 when every row has finished and nothing is buffered. */
 q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_frames, int32_t* done);
+/* Opt-in extension (no reference counterpart -- the reference decodes every chunk without left
+ * context, src/lib.rs:1755-1758, so streamed PCM differs from non-streamed PCM at chunk starts).  With
+ * left_context_frames = c > 0 each q3_stream_next decodes the previous min(c, frames so far) frames again in front of the
+ * chunk and drops their samples; every vocoder op is causal, so c < 0 (= the whole history) makes the streamed PCM
+ * identical to q3_vocode_session's, and a finite c bounds the extra work per chunk.  0 (default) = reference behaviour. */
+q3_status q3_session_set_stream_context(q3_session* s, int32_t left_context_frames);
 
 /* ref: Decoder12Hz::decode (src/models/codec/decoder_12hz.rs:411-505).  codes: i64 [B][16][T]
  * (host, the codes_to_tensor layout of src/lib.rs:1417-1431); pcm: f32 [B][T*1920] (host). */

@@ -103,6 +103,8 @@ struct SynthesisOptions {
   int32_t chunk_frames = 10;
   int32_t min_new_tokens = 2;
   std::optional<uint64_t> seed;
+  /* not in the reference (opt-in, see q3_session_set_stream_context): left-context frames per streamed chunk, -1 = all */
+  int32_t stream_left_context = 0;
 
   q3_gen_config to_gen_config() const {
     q3_gen_config g{};
@@ -754,6 +756,10 @@ class Session {
     if ((int32_t)seeds.size() != batch) throw Error(Q3_ERR_INVALID, "one seed per row is required");
     q3_gen_config g = o.to_gen_config();
     check(q3_session_create(m.handle(), batch, max_seq, &g, seeds.data(), &h_));
+    if (o.stream_left_context != 0) {
+      const q3_status st = q3_session_set_stream_context(h_, o.stream_left_context);
+      if (st != Q3_OK) { q3_session_destroy(h_); h_ = nullptr; check(st); }
+    }
   }
   ~Session() { if (h_) q3_session_destroy(h_); }
   Session(const Session&) = delete;

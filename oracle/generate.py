@@ -127,8 +127,12 @@ class StreamingSession:
     buffered codes are decoded INDEPENDENTLY (no vocoder state crosses chunks, lib.rs:1755-1758)."""
 
     def __init__(self, talker: Talker, cp: CodePredictor, decode_fn, prefill_embeds: torch.Tensor,
-                 text_ids: Sequence[int], cfg: smp.GenerationConfig, seed: int, chunk_frames: int = 10):
+                 text_ids: Sequence[int], cfg: smp.GenerationConfig, seed: int, chunk_frames: int = 10,
+                 left_context: int = 0):
         self.talker, self.cp, self.decode_fn, self.cfg = talker, cp, decode_fn, cfg
+        # left_context != 0 is the product's opt-in extension (q3_session_set_stream_context), restated here only so the
+        # tests can check it; 0 is the reference.  -1 = the whole history.
+        self.left_context = left_context
         self.ctx = smp.SamplingContext(seed)
         self.trailing, self.tlen, self.pad = talker.build_trailing_text(text_ids)
         self.caches = talker.new_kv_caches(cfg.max_new_tokens + 256)
@@ -155,7 +159,7 @@ class StreamingSession:
         if self.done:
             if self.frame_buffer:
                 buf, self.frame_buffer = self.frame_buffer, []
-                return self.decode_fn(codes_to_tensor(buf))
+                return self._decode_chunk(buf)
             return None
         while len(self.frame_buffer) < self.chunk_frames and self.frames_generated < self.cfg.max_new_tokens:
             if self.current_token is None:
@@ -187,7 +191,17 @@ class StreamingSession:
         if not self.frame_buffer:
             return None
         buf, self.frame_buffer = self.frame_buffer, []
-        return self.decode_fn(codes_to_tensor(buf))
+        return self._decode_chunk(buf)
+
+    def _decode_chunk(self, buf):
+        """lib.rs:1755-1758 decodes `buf` alone.  With left context c > 0 the c frames before it are decoded again in
+        front and their samples dropped (all vocoder ops are causal)."""
+        f0 = len(self.all_frames) - len(buf)
+        c = f0 if self.left_context < 0 else min(self.left_context, f0)
+        if c == 0:
+            return self.decode_fn(codes_to_tensor(buf))
+        pcm = self.decode_fn(codes_to_tensor(self.all_frames[f0 - c:]))
+        return pcm[c * 1920:]
 
     def is_done(self):
         return self.done and not self.frame_buffer

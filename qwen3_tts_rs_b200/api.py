@@ -46,6 +46,9 @@ class SynthesisOptions:
     chunk_frames: int = 10
     min_new_tokens: int = 2
     seed: Optional[int] = None
+    # Not in the reference (opt-in): frames of left context decoded again in front of every streamed
+    # chunk and dropped; -1 = the whole history (streamed PCM == non-streamed PCM), 0 = the reference's stateless chunks.
+    stream_left_context: int = 0
 
     def to_gen_config(self) -> L.GenConfig:
         g = L.GenConfig()
@@ -180,6 +183,8 @@ class Session:
         self.handle = C.c_void_p()
         sd = (C.c_uint64 * batch)(*[int(s) & ((1 << 64) - 1) for s in seeds])
         L.check(self.lib.q3_session_create(model.handle, batch, self.max_seq, C.byref(self.cfg), sd, C.byref(self.handle)))
+        if options.stream_left_context:
+            L.check(self.lib.q3_session_set_stream_context(self.handle, int(options.stream_left_context)))
 
     def reset(self, seeds: Sequence[int]):
         sd = (C.c_uint64 * self.B)(*[int(s) & ((1 << 64) - 1) for s in seeds])

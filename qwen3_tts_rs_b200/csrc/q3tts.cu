@@ -73,6 +73,7 @@ struct q3_session {
   uint64_t graph_launches = 0;     // kernels inside one replay of the frame graph
   // streaming
   std::vector<int> stream_emitted;
+  int stream_left_ctx = 0;         // frames of left context re-decoded per chunk (0 = the reference's stateless chunks)
   std::unique_ptr<VocoderScratch> voc;   // borrowed from the model's pool at the first vocode, returned on destruction
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
@@ -1337,24 +1338,30 @@ q3_status q3_generate(q3_session* s, int32_t max_frames, uint32_t* codes, int32_
   return q3_get_codes(s, max_frames, codes, n_frames);
 }
 
-// vocode frames [f0, f0+T) of every row (rows shorter than that are padded with their own frame 0.. and zeroed after)
-static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& row_len, float* pcm_host, size_t pcm_row_stride) {
+// vocode frames [f0, f0+T) of every row (rows shorter than that are padded with their own frame 0.. and zeroed after).
+// left_ctx > 0 (opt-in, q3_session_set_stream_context): frames [f0-c, f0) with c = min(left_ctx, f0) are decoded again as
+// left context and their samples dropped -- every vocoder op is causal, so with c == f0 the kept samples are exactly the
+// ones a single decode of the whole utterance produces.
+static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& row_len, float* pcm_host, size_t pcm_row_stride,
+                        int left_ctx = 0) {
   const q3_model* m = s->m;
   const int B = s->B, up = vocoder_total_upsample(m);
   if (T <= 0) return;
+  const int c = std::max(0, std::min(left_ctx, f0));
+  const int f0c = f0 - c, Tc = T + c;
   if (!s->voc) s->voc = m->acquire_scratch();
   DBuf& voc_codes = s->voc->codes;
   DBuf& voc_pcm = s->voc->pcm;
-  voc_codes.ensure((size_t)B * 16 * T * 8);
-  voc_pcm.ensure((size_t)B * T * up * 4);
+  voc_codes.ensure((size_t)B * 16 * Tc * 8);
+  voc_pcm.ensure((size_t)B * Tc * up * 4);
   // rows decode independently (the vocoder is causal per row), so one batched call over T frames and a
   // per-row truncation reproduces B separate Decoder12Hz::decode calls of length row_len[b].
-  vocoder_codes_to_tensor(s->codes.as<uint32_t>(), s->frames_cap, f0, T, B, voc_codes.as<long long>(), s->st);
-  vocoder_run(m, s->voc->ws, voc_codes.as<long long>(), B, T, voc_pcm.as<float>(), s->st);
+  vocoder_codes_to_tensor(s->codes.as<uint32_t>(), s->frames_cap, f0c, Tc, B, voc_codes.as<long long>(), s->st);
+  vocoder_run(m, s->voc->ws, voc_codes.as<long long>(), B, Tc, voc_pcm.as<float>(), s->st);
   if (pcm_host) {
     for (int b = 0; b < B; ++b) {
       const size_t n = (size_t)row_len[b] * up;
-      if (n) Q3_CHECK_CUDA(cudaMemcpyAsync(pcm_host + b * pcm_row_stride, voc_pcm.as<float>() + (size_t)b * T * up, n * 4,
+      if (n) Q3_CHECK_CUDA(cudaMemcpyAsync(pcm_host + b * pcm_row_stride, voc_pcm.as<float>() + ((size_t)b * Tc + c) * up, n * 4,
                                            cudaMemcpyDeviceToHost, s->st));
     }
     Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
@@ -1363,6 +1370,13 @@ static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& ro
       if (n < (size_t)T * up) memset(pcm_host + b * pcm_row_stride + n, 0, ((size_t)T * up - n) * 4);
     }
   }
+}
+
+q3_status q3_session_set_stream_context(q3_session* s, int32_t left_context_frames) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s, Q3_ERR_INVALID, "null session");
+  s->stream_left_ctx = left_context_frames < 0 ? INT32_MAX : left_context_frames;
+  Q3_API_END
 }
 
 q3_status q3_vocode_session(q3_session* s, int32_t max_frames, float* pcm) {
@@ -1418,7 +1432,7 @@ q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_
     for (int b = 0; b < B; ++b)
       if (len[b] > 0) { if (f0 < 0) f0 = s->stream_emitted[b]; else same = same && (f0 == s->stream_emitted[b]); }
     Q3_REQUIRE(same, Q3_ERR_STATE, "streaming rows out of step");
-    vocode_rows(s, f0, T, len, pcm, (size_t)chunk * up);
+    vocode_rows(s, f0, T, len, pcm, (size_t)chunk * up, s->stream_left_ctx);
     for (int b = 0; b < B; ++b)
       if (len[b] > 0)
         Q3_CHECK_CUDA(cudaMemcpyAsync(codes + (size_t)b * chunk * 16, s->codes.as<uint32_t>() + ((size_t)b * s->frames_cap + f0) * 16,

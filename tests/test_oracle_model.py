@@ -253,3 +253,30 @@ def test_streaming_session_chunks():
     assert [len(c) // 1920 for c in chunks] == [3, 3, 1]
     ref = OG.prefill_and_generate(tk, cp, emb, ids, cfg, 5)
     assert s.all_frames == ref
+
+
+def test_streaming_left_context_restores_the_non_streamed_waveform():
+    """The opt-in left-context streaming mode (q3_session_set_stream_context) on the oracle: every
+    vocoder op is causal, so re-decoding the whole history in front of each chunk and dropping its samples gives the
+    non-streamed waveform, while the reference's stateless chunks (left_context = 0) differ from it at chunk starts."""
+    spec = S.SPEC_TINY
+    w = talker_weights(spec)
+    tk, cp = OM.Talker(spec, w, OM.F32P), OM.CodePredictor(spec, w, OM.F32P)
+    voc = OV.Vocoder(spec.vocoder, vocoder_weights(spec.vocoder, spec.name))
+    dec = lambda c: voc.decode(c)[0, 0].numpy()
+    ids = W.synthetic_prompt(2, spec)
+    emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+    cfg = osmp.GenerationConfig(max_new_tokens=7)
+    runs = {}
+    for lc in (0, 2, -1):
+        s = OG.StreamingSession(tk, cp, dec, emb, ids, cfg, 5, chunk_frames=3, left_context=lc)
+        chunks = list(s)
+        assert [len(c) // 1920 for c in chunks] == [3, 3, 1]
+        runs[lc] = np.concatenate(chunks)
+    whole = dec(OG.codes_to_tensor(s.all_frames))
+    rms = float(np.sqrt(np.mean(whole ** 2)))
+    err = {lc: float(np.sqrt(np.mean((runs[lc] - whole) ** 2))) for lc in runs}
+    assert err[-1] <= 1e-6 * max(rms, 1e-3)                        # whole history: the non-streamed waveform
+    assert np.array_equal(runs[0][: 3 * 1920], runs[-1][: 3 * 1920])   # the first chunk has no history either way
+    assert err[0] > 1e-3 * rms                                     # stateless chunks do differ (the reference's behaviour)
+    assert err[2] < err[0]                                         # a bounded context already removes most of it

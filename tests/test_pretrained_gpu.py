@@ -35,3 +35,25 @@ def test_from_pretrained_equals_from_weights(tmp_path):
     back = api.AudioBuffer.load(str(tmp_path / "out.wav"))
     # x -> trunc(32767 x) / 32768: off by at most (|x| + 1) / 32768 for |x| <= 1
     assert len(back) == len(pb) and np.abs(back.samples - pb.samples).max() <= 2.0 / 32768 + 1e-7
+
+
+def test_streaming_left_context_matches_non_streamed_pcm():
+    """q3_session_set_stream_context (opt-in): with the whole history as left context the streamed PCM
+    equals the non-streamed PCM of the same run (tolerance 1e-6: the vocoder is causal and its results do not depend on
+    T, tests/test_gpu_vocoder.py); the default stays the reference's stateless chunks, which differ at chunk starts."""
+    spec = S.SPEC_TINY
+    tts = api.Qwen3TTS.from_weights(spec, talker_weights(spec), vocoder_weights(spec.vocoder, spec.name))
+    ids = W.synthetic_prompt(2, spec)
+    whole = tts.synthesize_with_voice([ids], options=api.SynthesisOptions(max_length=10), seeds=[99])[0].samples
+    out = {}
+    for lc in (0, 2, -1):
+        sess = tts.synthesize_streaming(ids, options=api.SynthesisOptions(max_length=10, chunk_frames=4, seed=99,
+                                                                          stream_left_context=lc))
+        chunks = list(sess)
+        assert sess.is_done() and sum(len(c) for c in chunks) == sess.frames_generated() * 1920 == len(whole)
+        out[lc] = np.concatenate([c.samples for c in chunks])
+    rms = float(np.sqrt(np.mean(whole ** 2)))
+    err = {lc: float(np.sqrt(np.mean((out[lc] - whole) ** 2))) for lc in out}
+    assert np.abs(out[-1] - whole).max() <= 1e-6, err
+    assert np.array_equal(out[0][: 4 * 1920], out[-1][: 4 * 1920])
+    assert err[0] > 1e-3 * rms and err[2] < err[0], err
