@@ -64,5 +64,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_host_example() -> str:
+    """Compile the C++ host mirror's example / test driver (include/q3tts.hpp over the C ABI) with g++ against the
+    freshly built library: the "does it build" check of the compiled host side."""
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "host_mirror_check.cpp")
+    out = os.path.join(root, "tests", "cpp", "host_mirror_check")
+    deps = [src, os.path.join(root, "include", "q3tts.hpp"), os.path.join(root, "include", "q3tts.h"), LIB]
+    if _stale(out, deps):
+        cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-I", os.path.join(root, "include"), src, "-o", out,
+               "-L", HERE, "-lq3tts_b200", f"-Wl,-rpath,{HERE}"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"g++ failed for {src}:\n{r.stderr[-4000:]}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
