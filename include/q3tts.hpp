@@ -75,7 +75,7 @@ inline std::optional<Speaker> speaker_from_name(std::string s) {
   static const std::map<std::string, Speaker> m = {
       {"serena", Speaker::Serena}, {"vivian", Speaker::Vivian}, {"uncle_fu", Speaker::UncleFu}, {"ryan", Speaker::Ryan},
       {"aiden", Speaker::Aiden},   {"ono_anna", Speaker::OnoAnna}, {"sohee", Speaker::Sohee},   {"eric", Speaker::Eric},
-      {"dylan", Speaker::Dylan}};
+      {"dylan", Speaker::Dylan},   {"unclefu", Speaker::UncleFu},  {"onoanna", Speaker::OnoAnna}};  // talker.rs:121-137
   auto it = m.find(s);
   return it == m.end() ? std::nullopt : std::optional<Speaker>(it->second);
 }
@@ -85,7 +85,9 @@ inline std::optional<Language> language_from_name(std::string s) {
       {"chinese", Language::Chinese}, {"english", Language::English}, {"japanese", Language::Japanese},
       {"korean", Language::Korean},   {"german", Language::German},   {"french", Language::French},
       {"russian", Language::Russian}, {"portuguese", Language::Portuguese}, {"spanish", Language::Spanish},
-      {"italian", Language::Italian}};
+      {"italian", Language::Italian}, {"en", Language::English}, {"zh", Language::Chinese}, {"ja", Language::Japanese},
+      {"ko", Language::Korean}, {"de", Language::German}, {"fr", Language::French}, {"ru", Language::Russian},
+      {"pt", Language::Portuguese}, {"es", Language::Spanish}, {"it", Language::Italian}};  // talker.rs:71-90
   auto it = m.find(s);
   return it == m.end() ? std::nullopt : std::optional<Language>(it->second);
 }

@@ -119,3 +119,24 @@ def test_weights_are_order_independent_and_named_like_the_checkpoint():
     assert "talker.code_predictor.small_to_mtp_projection.bias" in names
     assert "talker.code_predictor.small_to_mtp_projection.weight" not in {n for n, _, _ in W.talker_tensor_specs(S.SPEC_0_6B)}
     assert sum(int(np.prod(s)) for n, s, _ in W.vocoder_tensor_specs(S.VocoderSpec()) if "cluster_usage" not in n) > 100e6
+
+
+def test_rust_ffi_declares_every_symbol_of_the_header():
+    """rust/src/b200/ffi.rs is shipped as source (no Rust toolchain here): at least keep it in step with the header --
+    every q3_* function and both config structs' fields, in order."""
+    hdr = open(os.path.join(ROOT, "include", "q3tts.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "src", "b200", "ffi.rs")).read()
+    declared = set(re.findall(r"\b(q3_[a-z0-9_]+)\s*\(", hdr)) - {"q3_status"}
+    in_rust = set(re.findall(r"pub fn (q3_[a-z0-9_]+)\s*\(", rs))
+    assert declared == in_rust, declared ^ in_rust
+    for struct in ("q3_model_desc", "q3_gen_config", "q3_timing"):
+        body = re.search(r"typedef struct " + struct + r" \{(.*?)\} " + struct, hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        c_fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                c_fields += [re.sub(r"\[.*", "", f.strip()) for f in decl.split(None, 1)[1].split(",")]
+        rbody = re.search(r"pub struct " + struct + r" \{(.*?)\n\}", rs, re.S).group(1)
+        r_fields = re.findall(r"pub ([a-z0-9_]+):", rbody)
+        assert c_fields == r_fields, (struct, c_fields, r_fields)
