@@ -17,7 +17,7 @@ import pytest
 import torch
 
 from qwen3_tts_rs_b200 import api, spec as S, weights as W
-from helpers import bf16_ulp_diff, gpu_tts, oracle_models, oracle_run
+from helpers import bf16_ulp_diff, first_divergence_is_a_near_tie as _first_divergence_is_a_near_tie, gpu_tts, oracle_models, oracle_run
 
 pytestmark = pytest.mark.gpu
 
@@ -78,24 +78,6 @@ def test_prompt_assembly_and_trailing_text_on_device(spec):
     m, ok, why = _first_divergence_is_a_near_tie(got, frames, tr)
     print("match", m, why)
     assert ok and got[0][0] == frames[0][0], (m, why)      # first token depends only on the prefill
-
-
-def _first_divergence_is_a_near_tie(got, ref, tr):
-    """Returns (match_len, ok): ok is True when the sequences agree, or when the first position where they
-    differ is one where the oracle itself was within the stated margins (see module docstring)."""
-    n = min(len(got), len(ref))
-    for f in range(n):
-        if got[f] == ref[f]:
-            continue
-        g = next(i for i in range(16) if got[f][i] != ref[f][i])
-        if g == 0:       # semantic token = next_tok sampled at the end of frame f-1
-            margin = tr.frames[f - 1]["sample_margin"] if f > 0 else 0.0
-            return f, (f == 0) or margin <= 0.05, ("sample", f, margin)
-        ol = tr.frames[f]["cp_logits"][g - 1].float()
-        top2 = torch.topk(ol, 2).values
-        margin = float(top2[0] - top2[1])
-        return f, margin <= 2.0 ** -5 * abs(float(top2[0])) + 1e-6, ("argmax", f, g - 1, margin, float(top2[0]))
-    return n, len(got) == len(ref), ("length", len(got), len(ref))
 
 
 @pytest.mark.parametrize("spec", [S.SPEC_TINY, S.SPEC_MID], ids=lambda s: s.name)

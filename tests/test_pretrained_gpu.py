@@ -79,3 +79,30 @@ def test_cuda_path_against_the_committed_golden_vectors():
     assert abs(float(np.sqrt(np.mean(pcm.astype(np.float64) ** 2))) - v["rms"]) <= 1e-3
     codes = tts.generate_codes([fix["text_ids"]], options=api.SynthesisOptions(max_length=fix["frames"]), seeds=[fix["seed"]])[0]
     assert 1 <= len(codes) <= fix["frames"] and codes[0][0] == fix["bf16"]["codes"][0][0]
+
+
+def test_ragged_and_degenerate_prompts_in_one_batch():
+    """Edge cases of the prompt side in ONE ragged batch: empty text (9 prefill positions, trailing text = tts_eos only,
+    talker.rs:479-487 / lib.rs:509-516), a single text token (10 positions, trailing = tts_eos), an ordinary prompt and a
+    two-token one; rows of different prefill lengths are right-padded inside q3_prefill_ids.  Every row, in the batch and
+    run alone, must equal an independent oracle run up to the near-tie rule of test_gpu_model.py."""
+    from helpers import first_divergence_is_a_near_tie, gpu_tts, oracle_run
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec)
+    prompts = [[], [7], W.synthetic_prompt(4, spec), [11, 12]]
+    seeds = [5, 6, 7, 8]
+    opts = api.SynthesisOptions(max_length=8)
+    got = tts.generate_codes(prompts, options=opts, seeds=seeds)
+    report = []
+    for b, ids in enumerate(prompts):
+        ref, tr, emb = oracle_run(spec, ids, seeds[b], opts, trace=True)
+        assert emb.shape[1] == (10 if ids else 9)
+        assert got[b][0][0] == ref[0][0], (b, got[b][0], ref[0])         # first token depends on the prefill only
+        m, ok, why = first_divergence_is_a_near_tie(got[b], ref, tr)
+        report.append((b, m, ok, why))
+        solo = tts.generate_codes([ids], options=opts, seeds=[seeds[b]])[0]
+        m2, ok2, why2 = first_divergence_is_a_near_tie(solo, ref, tr)
+        assert ok2 and solo[0][0] == ref[0][0], (b, m2, why2)
+        report.append((b, "solo == batch row", solo == got[b]))
+    print("ragged batch (row, match_len, fork_is_near_tie, detail):", report)
+    assert all(r[2] for r in report if len(r) == 4), report
