@@ -60,3 +60,23 @@ def first_divergence_is_a_near_tie(got, ref, tr):
         margin = float(top2[0] - top2[1])
         return f, margin <= 2.0 ** -5 * abs(float(top2[0])) + 1e-6, ("argmax", f, g - 1, margin, float(top2[0]))
     return n, len(got) == len(ref), ("length", len(got), len(ref))
+
+
+def first_token_window(spec, text_ids, seed, opts, band=0.05, speaker="ryan", language="english"):
+    """The oracle's FIRST sampled token (drawn from the prefill logits, lib.rs:557-571) and the set of tokens whose CDF
+    interval meets [u - band, u + band] in the oracle's own distribution: bf16 logit noise of a few ulp moves the CDF by a few
+    percent, so the CUDA path may land on a neighbouring interval, but a wrong prompt would give an unrelated token (the
+    window holds ~10 % of the mass).  Stricter than the nearest-boundary margin, which is always small with ~40 survivors."""
+    tk, _ = oracle_models(spec)
+    emb = tk.custom_voice_embeds(text_ids, S.SPEAKER_IDS[speaker], S.LANGUAGE_IDS[language])
+    _, logits = tk.run_prefill_layers(emb, tk.new_kv_caches())
+    cfg = oracle_cfg(opts)
+    vocab = spec.codec_vocab
+    l2 = osmp.apply_generation_penalties(logits[:, 0].numpy().astype(np.float32), np.zeros((1, vocab), dtype=np.float32), cfg, 0,
+                                         osmp.build_suppression_mask(vocab, 2150))
+    u = float(osmp.SamplingContext(seed).rand_f32())
+    tok, dbg = osmp.sample_row(l2[0], cfg, np.float32(u), return_debug=True)
+    cum = np.cumsum(dbg["probs"].astype(np.float64))
+    lo = np.concatenate([[0.0], cum[:-1]])
+    window = {int(i) for i in np.nonzero((dbg["probs"] > 0) & (cum >= u - band) & (lo <= u + band))[0]}
+    return int(tok), window
