@@ -45,8 +45,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd = [_nvcc()] + NVCC_FLAGS + ["-c", sp, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(CSRC, os.path.basename(obj) + ".ptxas.log")
-        with open(log, "w") as f:
-            f.write(r.stderr)
+        with open(log, "w") as f:      # register / spill report, kept in the tree; compile times dropped so it is stable
+            f.write("".join(ln for ln in r.stderr.splitlines(True) if "Compile time" not in ln))
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {sp}:\n{r.stderr[-6000:]}")
         if verbose:
