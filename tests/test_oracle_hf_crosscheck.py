@@ -128,3 +128,44 @@ def test_vocoder_pre_transformer_matches_hf_code2wav():
             y = m(inputs_embeds=x).last_hidden_state
         mine = voc._rms(voc._transformer(x), w[pre + "norm.weight"])
         assert float((y - mine).abs().max()) <= 2e-5 * float(y.abs().max()), t
+
+
+def test_sampler_filters_match_hf_logits_processors():
+    """The reference's sampler algebra (sampling.rs:140-285, 375-400) restated in oracle/sampling.py against transformers'
+    independent logits processors on random rows: same repetition-penalty rule (positive logits divided, the rest
+    multiplied), same top-k survivor set, same nucleus (a token survives iff the probability mass of the strictly more
+    likely tokens is below p; HF states it from the other end of the sorted list).  Rows are continuous random values, so
+    ties -- where the reference's `>=` rules keep extras, tested separately -- do not occur."""
+    lp = pytest.importorskip("transformers.generation.logits_process")
+    import numpy as np
+    from oracle import sampling as osmp
+    rng = np.random.default_rng(3)
+    for trial in range(40):
+        v = 3072 if trial % 2 else 2048
+        row = (rng.standard_normal(v) * (1.0 + trial % 5)).astype(np.float32)
+        t = torch.from_numpy(row)[None]
+        # repetition penalty over a random seen-set
+        seen = rng.choice(v, size=50, replace=False)
+        mask = np.zeros((1, v), dtype=np.float32)
+        mask[0, seen] = 1.0
+        mine = osmp.apply_repetition_penalty_with_mask(row[None].copy(), mask, 1.05)[0]
+        hf = lp.RepetitionPenaltyLogitsProcessor(1.05)(torch.from_numpy(seen)[None], t.clone())[0].numpy()
+        assert np.allclose(mine, hf, rtol=3e-7, atol=0)            # x * (1/p) vs x / p: one rounding apart
+        # top-k
+        k = int(rng.integers(1, 100))
+        mine_k = osmp.top_k_filter(row.copy(), k)
+        hf_k = lp.TopKLogitsWarper(top_k=k)(None, t.clone())[0].numpy()
+        assert np.array_equal(np.isfinite(mine_k), np.isfinite(hf_k)) and int(np.isfinite(mine_k).sum()) == k
+        # nucleus, on the temperature-scaled row as the reference applies it (sampling.rs:148-171)
+        p = float(rng.choice([0.3, 0.5, 0.9, 0.95]))
+        scaled = (row * np.float32(1.0 / 0.9)).astype(np.float32)
+        mine_p = np.isfinite(osmp.top_p_filter(scaled.copy(), p, "gpu"))
+        hf_p = np.isfinite(lp.TopPLogitsWarper(top_p=p)(None, torch.from_numpy(scaled)[None].clone())[0].numpy())
+        diff = np.nonzero(mine_p != hf_p)[0]
+        if diff.size:                                              # only a token sitting on the p boundary may differ (f32 cumsum order)
+            probs = osmp.softmax_f32(scaled)
+            order = np.argsort(-probs)
+            excl = np.concatenate([[0.0], np.cumsum(probs[order].astype(np.float64))[:-1]])
+            pos = {int(tok): i for i, tok in enumerate(order)}
+            assert diff.size == 1 and abs(excl[pos[int(diff[0])]] - p) < 1e-5, (trial, diff, p)
+        assert mine_p.sum() >= 1 and mine_p[np.argmax(scaled)]
