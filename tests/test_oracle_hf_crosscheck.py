@@ -169,3 +169,38 @@ def test_sampler_filters_match_hf_logits_processors():
             pos = {int(tok): i for i, tok in enumerate(order)}
             assert diff.size == 1 and abs(excl[pos[int(diff[0])]] - p) < 1e-5, (trial, diff, p)
         assert mine_p.sum() >= 1 and mine_p[np.argmax(scaled)]
+
+
+def test_rvq_dequantisation_matches_hf_mimi_split_rvq():
+    """decoder_12hz.rs:199-225, 411-455: codebook = embedding_sum / clamp(cluster_usage), one semantic + 15 acoustic
+    codebooks summed per group, a bias-free 1x1 output projection per group, the two groups added -- the Mimi split RVQ.
+    transformers' `MimiSplitResidualVectorQuantizer.decode` is an independent implementation of it; cluster_usage is
+    drawn away from 1 here so the division is exercised (the synthetic checkpoints use 1)."""
+    mm = pytest.importorskip("transformers.models.mimi.modeling_mimi")
+    from transformers.models.mimi.configuration_mimi import MimiConfig
+    from oracle import generate as OG, vocoder as OV
+    v = S.TINY_VOCODER
+    g = torch.Generator().manual_seed(4)
+    w = dict(W.make_vocoder_weights(v))
+    for k in list(w):
+        if k.endswith("cluster_usage"):
+            w[k] = 0.5 + 2.5 * torch.rand(w[k].shape, generator=g)
+    cfg = MimiConfig(codebook_size=v.codebook_size, codebook_dim=v.vq_dim, vector_quantization_hidden_dimension=v.vq_dim,
+                     hidden_size=v.codebook_dim, num_quantizers=v.num_quantizers, num_semantic_quantizers=1)
+    q = mm.MimiSplitResidualVectorQuantizer(cfg).eval()
+    sd = {}
+    for grp, hf in (("rvq_first", "semantic_residual_vector_quantizer"), ("rvq_rest", "acoustic_residual_vector_quantizer")):
+        n = 1 if grp == "rvq_first" else v.num_quantizers - 1
+        for i in range(n):
+            sd[f"{hf}.layers.{i}.codebook.embed_sum"] = w[f"decoder.quantizer.{grp}.vq.layers.{i}._codebook.embedding_sum"]
+            sd[f"{hf}.layers.{i}.codebook.cluster_usage"] = w[f"decoder.quantizer.{grp}.vq.layers.{i}._codebook.cluster_usage"]
+        sd[f"{hf}.output_proj.weight"] = w[f"decoder.quantizer.{grp}.output_proj.weight"]
+    missing = q.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all("input_proj" in k or "initialized" in k for k in missing.missing_keys), missing
+    codes = torch.randint(0, v.codebook_size, (2, v.num_quantizers, 9), generator=g)
+    with torch.no_grad():
+        want = q.decode(codes)                                     # [B, codebook_dim, T]
+    stages = {}
+    OV.Vocoder(v, w).decode(codes.numpy(), stages)
+    got = stages["quantized"]
+    assert got.shape == want.shape and float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
