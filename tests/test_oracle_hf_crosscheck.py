@@ -204,3 +204,40 @@ def test_rvq_dequantisation_matches_hf_mimi_split_rvq():
     OV.Vocoder(v, w).decode(codes.numpy(), stages)
     got = stages["quantized"]
     assert got.shape == want.shape and float((got - want).abs().max()) <= 2e-5 * float(want.abs().max())
+
+
+def test_code_predictor_wiring_matches_hf_omni_code_predictor():
+    """Which table feeds which pass (code_predictor.rs:320-416): pass 0 sees [talker hidden, semantic embedding] and reads
+    lm_head[0] at position 1; pass g >= 1 embeds the previous code with codec_embedding[g-1] and reads lm_head[g].
+    transformers' Qwen3-Omni talker code predictor (same model family) encodes that wiring inside its own forward
+    (`generation_steps`): driven greedily on the oracle's weights it must emit the oracle's 15 codes."""
+    mm = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    cc = pytest.importorskip("transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe")
+    spec = S.SPEC_TINY                                             # talker hidden == CP hidden: no projection, as in Omni
+    w = W.make_talker_weights(spec, dtype=torch.float32)
+    cfg = cc.Qwen3OmniMoeTalkerCodePredictorConfig(
+        vocab_size=spec.cp_vocab, hidden_size=spec.cp_hidden, intermediate_size=spec.cp_inter, num_hidden_layers=spec.cp_layers,
+        num_attention_heads=spec.cp_heads, num_key_value_heads=spec.cp_kv_heads, head_dim=spec.head_dim,
+        rms_norm_eps=spec.rms_eps, rope_parameters={"rope_type": "default", "rope_theta": spec.rope_theta},
+        attention_bias=False, num_code_groups=spec.groups, max_position_embeddings=1024, use_sliding_window=False)
+    cfg._attn_implementation = "eager"
+    m = mm.Qwen3OmniMoeTalkerCodePredictorModelForConditionalGeneration(cfg).eval().to(torch.float32)
+    pre = "talker.code_predictor."
+    sd = {k[len(pre):]: v for k, v in w.items() if k.startswith(pre)}
+    m.load_state_dict(sd, strict=True)
+    cp = OM.CodePredictor(spec, w, OM.F32P)
+    g = torch.Generator().manual_seed(21)
+    for trial in range(3):
+        talker_hidden = torch.randn(1, 1, spec.hidden, generator=g)
+        sem = w["talker.model.codec_embedding.weight"][100 + trial][None, None]
+        codes, logits = cp.generate_acoustic_codes(talker_hidden, sem, cp.new_kv_caches(), return_logits=True)
+        with torch.no_grad():
+            o = m(inputs_embeds=torch.cat([talker_hidden, sem], 1), use_cache=True)
+            hf_codes = [int(torch.argmax(o.logits[0, -1]))]
+            assert float((o.logits[0, -1] - logits[0]).abs().max()) <= 5e-5 * float(logits[0].abs().max())
+            for step in range(1, spec.groups - 1):
+                o = m(input_ids=torch.tensor([[hf_codes[-1]]]), past_key_values=o.past_key_values, use_cache=True,
+                      generation_steps=step, position_ids=torch.tensor([[step + 1]]))
+                assert float((o.logits[0, -1] - logits[step]).abs().max()) <= 5e-5 * float(logits[step].abs().max()), step
+                hf_codes.append(int(torch.argmax(o.logits[0, -1])))
+        assert hf_codes == codes, trial
