@@ -463,15 +463,35 @@ class Parser {
         case 'b': out.push_back('\b'); break;
         case 'f': out.push_back('\f'); break;
         case 'u': {
-          if (p_ + 4 > t_.size()) fail("bad \\u escape");
-          unsigned cp = (unsigned)std::stoul(t_.substr(p_, 4), nullptr, 16);
-          p_ += 4;
+          auto hex4 = [&]() -> unsigned {
+            if (p_ + 4 > t_.size()) fail("bad \\u escape");
+            unsigned v = 0;
+            for (int i = 0; i < 4; ++i) {
+              const char h = t_[p_++];
+              v <<= 4;
+              if (h >= '0' && h <= '9') v |= (unsigned)(h - '0');
+              else if (h >= 'a' && h <= 'f') v |= (unsigned)(h - 'a' + 10);
+              else if (h >= 'A' && h <= 'F') v |= (unsigned)(h - 'A' + 10);
+              else fail("bad \\u escape");
+            }
+            return v;
+          };
+          unsigned cp = hex4();
+          if (cp >= 0xD800 && cp <= 0xDBFF && p_ + 1 < t_.size() && t_[p_] == '\\' && t_[p_ + 1] == 'u') {  // surrogate pair
+            const size_t save = p_;
+            p_ += 2;
+            const unsigned lo = hex4();
+            if (lo >= 0xDC00 && lo <= 0xDFFF) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+            else p_ = save;
+          }
           if (cp < 0x80) out.push_back((char)cp);
           else if (cp < 0x800) { out.push_back((char)(0xC0 | (cp >> 6))); out.push_back((char)(0x80 | (cp & 0x3F))); }
-          else { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+          else if (cp < 0x10000) { out.push_back((char)(0xE0 | (cp >> 12))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
+          else { out.push_back((char)(0xF0 | (cp >> 18))); out.push_back((char)(0x80 | ((cp >> 12) & 0x3F))); out.push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out.push_back((char)(0x80 | (cp & 0x3F))); }
           break;
         }
-        default: out.push_back(e);
+        case '"': case '\\': case '/': out.push_back(e); break;
+        default: fail("bad escape");
       }
     }
     if (p_ >= t_.size()) fail("unterminated string");

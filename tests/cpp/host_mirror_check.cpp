@@ -1,6 +1,7 @@
 // Driver for tests/test_cpp_host.py: exercises include/q3tts.hpp (the C++ host mirror) and prints machine-readable
 // lines that the test compares with the Python mirror (qwen3_tts_rs_b200/api.py, formats.py).
 #include <cinttypes>
+#include <functional>
 #include <iostream>
 #include <sstream>
 
@@ -90,6 +91,41 @@ int main(int argc, char** argv) {
       if (c.mrope_section) std::printf("mrope %zu %zu %zu\n", (*c.mrope_section)[0], (*c.mrope_section)[1], (*c.mrope_section)[2]);
       else std::printf("mrope none\n");
       std::printf("speaker_enc_dim %ld\n", c.speaker_enc_dim ? (long)*c.speaker_enc_dim : -1L);
+      return 0;
+    }
+    if (mode == "json") {  // json <file>: parse and print a canonical one-line form (strings as hex, numbers as int / %.17g)
+      auto raw = read_file(argv[2]);
+      const json::Value v = json::parse(std::string(raw.begin(), raw.end()));
+      std::function<void(const json::Value&)> dump = [&](const json::Value& x) {
+        switch (x.kind) {
+          case json::Value::Null: std::printf("n"); break;
+          case json::Value::Bool: std::printf(x.b ? "t" : "f"); break;
+          case json::Value::Int: std::printf("i%" PRId64, x.i); break;
+          case json::Value::Float: std::printf("d%.17g", x.d); break;
+          case json::Value::String:
+            std::printf("s");
+            for (unsigned char c : x.s) std::printf("%02x", c);
+            break;
+          case json::Value::Array:
+            std::printf("[");
+            for (const auto& e : x.a) { dump(e); std::printf(","); }
+            std::printf("]");
+            break;
+          case json::Value::Obj:
+            std::printf("{");
+            for (const auto& kv : x.o) {
+              std::printf("s");
+              for (unsigned char c : kv.first) std::printf("%02x", c);
+              std::printf(":");
+              dump(kv.second);
+              std::printf(",");
+            }
+            std::printf("}");
+            break;
+        }
+      };
+      dump(v);
+      std::printf("\n");
       return 0;
     }
     if (mode == "safetensors") {  // safetensors <file>

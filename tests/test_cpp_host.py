@@ -185,3 +185,65 @@ def test_cpp_and_python_mirrors_generate_identical_output(exe, tmp_path):
     assert int(info["chunks"]) == -(-len(codes) // 3)
     back = api.AudioBuffer.load(out_dir + "/audio.wav")
     assert len(back) == len(audio) and np.abs(back.samples - audio.samples).max() <= 2.0 / 32768 + 1e-7
+
+
+def _canon(x):
+    """The canonical form the C++ driver prints in `json` mode."""
+    if x is None:
+        return "n"
+    if x is True:
+        return "t"
+    if x is False:
+        return "f"
+    if isinstance(x, int):
+        return f"i{x}"
+    if isinstance(x, float):
+        return "d%.17g" % x
+    if isinstance(x, str):
+        return "s" + x.encode("utf-8").hex()
+    if isinstance(x, list):
+        return "[" + "".join(_canon(e) + "," for e in x) + "]"
+    return "{" + "".join("s" + k.encode("utf-8").hex() + ":" + _canon(v) + "," for k, v in x.items()) + "}"
+
+
+def test_cpp_json_parser_agrees_with_python_and_rejects_damage(exe, tmp_path):
+    """The header-only JSON parser reads config.json and safetensors headers, i.e. files from outside: random documents
+    must parse to what Python's json module sees, and every truncation of a document must be an error (exit 11), never a
+    crash or a silent partial parse."""
+    import random
+    rnd = random.Random(5)
+    alphabet = ["a", "Z", "0", " ", "_", ".", "é", "雪", "\U0001F600", "\\", "\"", "/", "\n", "\t", " ", "{", "]", ":"]
+
+    def rand_str():
+        return "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 8)))
+
+    def rand_val(depth):
+        k = rnd.randint(0, 9 if depth < 4 else 6)
+        if k == 0:
+            return None
+        if k == 1:
+            return rnd.random() < 0.5
+        if k in (2, 3):
+            return rnd.choice([0, -1, 7, 2048, 151936, -2 ** 40, 2 ** 53, rnd.randint(-10 ** 9, 10 ** 9)])
+        if k in (4, 5):
+            return rnd.choice([0.5, -1e-06, 1000000.0, 1e-5, 3.141592653589793, -2.5e+300, 1e-300, rnd.uniform(-1e6, 1e6)])
+        if k == 6:
+            return rand_str()
+        if k in (7, 8):
+            return [rand_val(depth + 1) for _ in range(rnd.randint(0, 4))]
+        return {rand_str() + str(i): rand_val(depth + 1) for i in range(rnd.randint(0, 4))}
+
+    p = tmp_path / "doc.json"
+    for trial in range(60):
+        doc = {"k" + str(i): rand_val(0) for i in range(rnd.randint(1, 5))}
+        text = json.dumps(doc, ensure_ascii=bool(trial % 2), indent=(None, 1, 2)[trial % 3])
+        p.write_text(text, encoding="utf-8")
+        assert run(exe, "json", p).stdout.strip() == _canon(json.loads(text)), text
+    text = json.dumps({"a": [1, 2.5, {"b": "x\\\"y", "c": None}], "d": {"e": [True, False]}, "f": "é雪"})
+    for cut in range(len(text) - 1):
+        p.write_text(text[:cut], encoding="utf-8")
+        r = run(exe, "json", p, ok=False)
+        assert r.returncode == 11, (cut, text[:cut], r.returncode, r.stderr)
+    for bad in ('{"a": 1,}', '{"a" 1}', '[1 2]', '{"a": tru}', '{"a": 1} x', '{"a": "\\u12"}', '{"a": -}', '{1: 2}', '{"a": "\\u12zz"}', '{"a": "\\q"}'):
+        p.write_text(bad)
+        assert run(exe, "json", p, ok=False).returncode == 11, bad
