@@ -667,7 +667,14 @@ class SafeTensorsFile {
         e.end = (size_t)off.a[1].as_u64().value_or(0);
         const size_t es = elem_size(e.dtype);
         if (es == 0) throw Error(Q3_ERR_UNSUPPORTED, path + ": tensor " + kv.first + " has unsupported dtype " + e.dtype);
-        if (e.begin > e.end || e.end > size_ - base_ || e.end - e.begin != e.numel() * es)
+        // element count with overflow guard: a crafted shape must not wrap around to a plausible byte count
+        size_t count = 1;
+        bool overflow = false;
+        for (int64_t dim : e.shape) {
+          if (dim < 0 || (dim != 0 && count > size_ / (size_t)dim)) { overflow = true; break; }
+          count *= (size_t)dim;
+        }
+        if (overflow || e.begin > e.end || e.end > size_ - base_ || e.end - e.begin != count * es)
           throw Error(Q3_ERR_INVALID, path + ": tensor " + kv.first + " has bad data_offsets");
         entries_.emplace(kv.first, std::move(e));
       }

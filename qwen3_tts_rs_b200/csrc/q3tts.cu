@@ -823,6 +823,14 @@ q3_status q3_model_set_tensor(q3_model* m, const char* hf_name, const void* data
   Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
   std::string name(hf_name);
   RawTensor t;
+  {
+    size_t cnt = 1;        // refuse shapes whose element count would wrap around (headers come from files)
+    for (int i = 0; i < ndim; ++i) {
+      Q3_REQUIRE(shape[i] >= 0 && (shape[i] == 0 || cnt <= ((size_t)1 << 40) / (size_t)shape[i]), Q3_ERR_INVALID,
+                 "tensor shape out of range");
+      cnt *= (size_t)shape[i];
+    }
+  }
   t.shape.assign(shape, shape + ndim);
   const size_t n = t.numel();
   const bool is_voc = name.rfind("decoder.", 0) == 0;

@@ -21,6 +21,7 @@ Host-side byte work only: nothing here touches the GPU, and nothing here imports
 from __future__ import annotations
 
 import json
+import math
 import os
 import struct
 from dataclasses import dataclass
@@ -236,14 +237,20 @@ def read_safetensors_header(path: str) -> Tuple[Dict[str, dict], int]:
         if n > size - 8 or n > 100_000_000:
             raise ValueError(f"{path}: header length {n} is out of range")
         hdr = json.loads(f.read(n).decode("utf-8"))
+    if not isinstance(hdr, dict):
+        raise ValueError(f"{path}: header is not a JSON object")
     hdr.pop("__metadata__", None)
     base = 8 + n
     for name, e in hdr.items():
+        if not isinstance(e, dict) or not {"dtype", "shape", "data_offsets"} <= set(e):
+            raise ValueError(f"{path}: tensor {name} lacks dtype / shape / data_offsets")
         dt = _ST_DTYPES.get(e["dtype"])
         if dt is None:
             raise ValueError(f"{path}: tensor {name} has unsupported dtype {e['dtype']}")
         b, end = e["data_offsets"]
-        numel = int(np.prod(e["shape"])) if e["shape"] else 1
+        if not all(isinstance(d, int) and not isinstance(d, bool) and d >= 0 for d in e["shape"]):
+            raise ValueError(f"{path}: tensor {name} has a bad shape {e['shape']}")
+        numel = math.prod(e["shape"])                       # Python ints: a crafted shape cannot wrap around
         want = numel * torch.empty(0, dtype=dt).element_size()
         if not (0 <= b <= end <= size - base) or end - b != want:
             raise ValueError(f"{path}: tensor {name} has bad data_offsets {e['data_offsets']} for {e['dtype']}{e['shape']}")

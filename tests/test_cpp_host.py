@@ -140,6 +140,22 @@ def test_safetensors_mapping_matches(exe, tmp_path):
     raw = open(str(tmp_path / "ours.safetensors"), "rb").read()
     open(p, "wb").write(raw[:-4])
     assert run(exe, "safetensors", p, ok=False).returncode == 10 + 1
+    import struct
+    for hdr in ({"w": {"dtype": "F32", "shape": [4, 4], "data_offsets": [0, 60]}},                  # size disagrees with dtype x shape
+                {"w": {"dtype": "F32", "shape": [4, 4], "data_offsets": [64, 128]}},                 # beyond the file
+                {"w": {"dtype": "F32", "shape": [2 ** 32, 2 ** 32], "data_offsets": [0, 0]}},        # element count wraps to 0
+                {"w": {"dtype": "F32", "shape": [2 ** 62, 4], "data_offsets": [0, 0]}},
+                {"w": {"dtype": "F8_E4M3", "shape": [4], "data_offsets": [0, 4]}},                   # dtype the decode path does not take
+                {"w": {"dtype": "F32", "shape": [4]}},                                               # no offsets
+                [1, 2, 3]):
+        js = json.dumps(hdr).encode()
+        open(p, "wb").write(struct.pack("<Q", len(js)) + js + b"\0" * 64)
+        r = run(exe, "safetensors", p, ok=False)
+        assert r.returncode in (10 + 1, 10 + 6), (hdr, r.returncode, r.stderr)
+        with pytest.raises(ValueError):                       # the Python reader refuses the same files
+            F.load_safetensors(p)
+    open(p, "wb").write(struct.pack("<Q", 2 ** 63) + b"{}")
+    assert run(exe, "safetensors", p, ok=False).returncode == 10 + 1
 
 
 def test_from_pretrained_fails_loudly_without_a_gpu(exe, tmp_path):
