@@ -93,6 +93,11 @@ int main(int argc, char** argv) {
       std::printf("speaker_enc_dim %ld\n", c.speaker_enc_dim ? (long)*c.speaker_enc_dim : -1L);
       return 0;
     }
+    if (mode == "wav") {  // wav <file>: rate, sample count, hash of the f32 samples
+      AudioBuffer w = AudioBuffer::load(argv[2]);
+      std::printf("%u %zu %016" PRIx64 "\n", w.sample_rate, w.len(), fnv1a((const uint8_t*)w.samples.data(), w.len() * 4));
+      return 0;
+    }
     if (mode == "json") {  // json <file>: parse and print a canonical one-line form (strings as hex, numbers as int / %.17g)
       auto raw = read_file(argv[2]);
       const json::Value v = json::parse(std::string(raw.begin(), raw.end()));

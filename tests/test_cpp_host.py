@@ -263,3 +263,61 @@ def test_cpp_json_parser_agrees_with_python_and_rejects_damage(exe, tmp_path):
     for bad in ('{"a": 1,}', '{"a" 1}', '[1 2]', '{"a": tru}', '{"a": 1} x', '{"a": "\\u12"}', '{"a": -}', '{1: 2}', '{"a": "\\u12zz"}', '{"a": "\\q"}'):
         p.write_text(bad)
         assert run(exe, "json", p, ok=False).returncode == 11, bad
+
+
+def _fnv(b):
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & (2 ** 64 - 1)
+    return h
+
+
+def test_wav_readers_agree_on_valid_and_damaged_files(exe, tmp_path):
+    """io.rs:110-141 in both mirrors: for PCM 8/16/24/32, float32, mono and multi-channel files, and for the same files
+    with bytes flipped or cut, the two readers either both refuse the file or return the same rate, length and samples."""
+    import random
+    import struct
+    rnd = random.Random(9)
+    p = str(tmp_path / "f.wav")
+
+    def wav(tag, channels, rate, bits, payload, extra=b""):
+        fmt = struct.pack("<HHIIHH", tag, channels, rate, rate * channels * bits // 8, channels * bits // 8, bits)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + extra + b"data" + struct.pack("<I", len(payload)) + payload
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    files = []
+    for bits in (8, 16, 24, 32):
+        for ch in (1, 2, 3):
+            files.append(wav(1, ch, 24000, bits, bytes(rnd.randrange(256) for _ in range(ch * (bits // 8) * 11))))
+    files.append(wav(3, 1, 16000, 32, np.linspace(-1, 1, 17, dtype="<f4").tobytes()))
+    files.append(wav(3, 2, 48000, 32, np.linspace(-1, 1, 18, dtype="<f4").tobytes(), extra=b"LIST" + struct.pack("<I", 5) + b"abcde\0"))
+    files.append(wav(1, 1, 24000, 16, b""))
+    damaged = []
+    for f in files:
+        for _ in range(6):
+            g = bytearray(f)
+            if rnd.random() < 0.5 and len(g) > 13:
+                g = g[: rnd.randrange(12, len(g))]
+            for _ in range(rnd.randint(1, 3)):
+                g[rnd.randrange(len(g))] = rnd.randrange(256)
+            damaged.append(bytes(g))
+    agree = refused = 0
+    for data in files + damaged:
+        open(p, "wb").write(data)
+        r = run(exe, "wav", p, ok=False)
+        try:
+            x, rate = F.load_wav(p)
+            py = (rate, x.size, _fnv(x.astype("<f4").tobytes()))
+        except (ValueError, OSError, struct.error, ZeroDivisionError):
+            py = None
+        if py is None:
+            assert r.returncode in (11, 16), (r.returncode, r.stderr, data[:64])
+            refused += 1
+        else:
+            assert r.returncode == 0, (r.stderr, data[:64])
+            rate_c, n_c, h_c = r.stdout.split()
+            assert (int(rate_c), int(n_c)) == py[:2], (r.stdout, py, data[:64])
+            if not np.isnan(x).any():                             # NaN payload bits may differ; everything else must not
+                assert int(h_c, 16) == py[2], (r.stdout, py, data[:64])
+            agree += 1
+    assert agree >= len(files) and refused >= 1, (agree, refused)
