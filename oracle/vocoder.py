@@ -135,6 +135,12 @@ class Vocoder:
 
     def decode(self, codes, stages: Optional[dict] = None) -> torch.Tensor:
         """codes: i64 [B,16,T] -> f32 [B,1,T*1920] in [-1,1] (decoder_12hz.rs:411-505)."""
+        return self.decode_back(self.decode_front(codes, stages), stages)
+
+    def decode_front(self, codes, stages: Optional[dict] = None) -> torch.Tensor:
+        """First half of `decode`, everything at the frame rate: RVQ de-quantisation, pre_conv, pre-transformer, output
+        projection -> [B, latent, T].  (The split into front / back is not in the reference; it exists so that tests can
+        measure how much left context the convolutional back half needs -- see test_vocoder_back_half_receptive_field.)"""
         v, w = self.v, self.w
         codes = torch.as_tensor(np.asarray(codes), dtype=torch.long)
         bsz, nq, t = codes.shape
@@ -156,7 +162,12 @@ class Vocoder:
         h = self._rms(h, w["decoder.pre_transformer.norm.weight"])
         h = h @ w["decoder.pre_transformer.output_proj.weight"].t() + w["decoder.pre_transformer.output_proj.bias"]
         st["output_proj"] = h
-        h = h.transpose(1, 2)
+        return h.transpose(1, 2)
+
+    def decode_back(self, h, stages: Optional[dict] = None) -> torch.Tensor:
+        """Second half: the causal convolutional upsampler, [B, latent, T] -> [B, 1, T*1920]."""
+        v, w = self.v, self.w
+        st = stages if stages is not None else {}
         for s, ratio in enumerate(v.upsampling_ratios):
             p = f"decoder.upsample.{s}"
             h = causal_trans_conv1d(h, w[f"{p}.0.conv.weight"], w[f"{p}.0.conv.bias"], ratio)

@@ -280,3 +280,31 @@ def test_streaming_left_context_restores_the_non_streamed_waveform():
     assert np.array_equal(runs[0][: 3 * 1920], runs[-1][: 3 * 1920])   # the first chunk has no history either way
     assert err[0] > 1e-3 * rms                                     # stateless chunks do differ (the reference's behaviour)
     assert err[2] < err[0]                                         # a bounded context already removes most of it
+
+
+def test_vocoder_back_half_receptive_field():
+    """How much left context an exact streamed decode needs.  The front half of the vocoder (RVQ, pre_conv, pre-transformer)
+    runs at the frame rate and attends to the whole history; the back half is a causal conv stack whose look-back adds up
+    to 6/2 + 6/4 + 6/4 (ConvNeXt k7 x2, init conv k7) + 1/4 + 78/32 + 1/32 + 78/160 + 1/160 + 78/640 + 1/640 + 78/1920 +
+    6/1920 = 9.4 frames (residual units: k7 with dilation 1, 3, 9 = 78 samples per block; transposed convs k = 2s: one input
+    sample).  So: front half over the whole history + back half over the chunk and the 10 frames before it reproduces the
+    non-streamed waveform exactly, and 9 frames do not.  (Design input for the stateful streaming vocoder)"""
+    v = S.TINY_VOCODER                                              # same kernel sizes, dilations and rates as the full model
+    assert (v.upsampling_ratios, v.upsample_rates) == (S.VocoderSpec().upsampling_ratios, S.VocoderSpec().upsample_rates)
+    # float64 copy of the weights: in f32 the taps furthest back contribute less than the summation-order noise of the conv
+    # routines (~5e-7), which would blur the boundary this test is about
+    voc = OV.Vocoder(v, vocoder_weights(v, "tiny"))
+    g = torch.Generator().manual_seed(8)
+    codes = torch.randint(0, v.codebook_size, (1, 16, 26), generator=g).numpy()
+    front = voc.decode_front(codes).double()                        # [1, latent, 26], whole history
+    voc.w = {k: t.double() for k, t in voc.w.items()}              # back half in f64 from here on
+    whole = voc.decode_back(front)[0, 0]
+    f0, t = 20, 6                                                   # stream the last 6 frames
+    want = whole[f0 * 1920:]
+    err = {}
+    for c in (0, 4, 9, 10, 12):
+        part = voc.decode_back(front[:, :, f0 - c:])[0, 0][c * 1920:]
+        assert part.shape == want.shape
+        err[c] = float((part - want).abs().max())
+    assert err[10] <= 1e-13 and err[12] <= 1e-13, err               # exact: nothing outside the window is read
+    assert err[9] > 1e-11 and err[4] > err[9] and err[0] > err[4], err
