@@ -241,3 +241,41 @@ def test_code_predictor_wiring_matches_hf_omni_code_predictor():
                 assert float((o.logits[0, -1] - logits[step]).abs().max()) <= 5e-5 * float(logits[step].abs().max()), step
                 hf_codes.append(int(torch.argmax(o.logits[0, -1])))
         assert hf_codes == codes, trial
+
+
+def test_vocoder_back_half_matches_hf_code2wav_stack():
+    """The whole convolutional back half of the vocoder (decoder_12hz.rs:457-505: 2 x [transposed conv, ConvNeXt], init conv,
+    4 decoder blocks of SnakeBeta + transposed conv + 3 residual units, final SnakeBeta + conv, clamp) against the
+    `upsample` + `decoder` stacks of transformers' `Qwen3OmniMoeCode2Wav`, with all 140 tensors loaded BY NAME from the
+    oracle's checkpoint layout.  The one known difference: transformers trims a transposed conv on both sides, the Rust
+    reference on the right only (causal_trans_conv.rs:86-100) and keeps exactly T*1920 samples -- the reference wins.  Both
+    stacks are causal and their right ends coincide, so the waveforms must agree sample for sample once the differing left
+    edge (555 samples shorter in transformers) has left the 10-frame receptive field."""
+    mm = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    cc = pytest.importorskip("transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe")
+    from oracle import vocoder as OV
+    v = S.TINY_VOCODER
+    w = W.make_vocoder_weights(v)
+    cfg = cc.Qwen3OmniMoeCode2WavConfig(hidden_size=v.latent_dim, num_attention_heads=4, num_key_value_heads=4, intermediate_size=64,
+                                        num_hidden_layers=1, decoder_dim=v.decoder_dim, upsample_rates=v.upsample_rates,
+                                        upsampling_ratios=v.upsampling_ratios, codebook_size=64, num_quantizers=2)
+    m = mm.Qwen3OmniMoeCode2Wav(cfg).eval()
+    keys = [k for k in m.state_dict() if k.startswith(("upsample.", "decoder."))]
+    assert len(keys) == 140
+    res = m.load_state_dict({k: w["decoder." + k] for k in keys}, strict=False)
+    assert not res.unexpected_keys and not any(k.startswith(("upsample.", "decoder.")) for k in res.missing_keys)
+    g = torch.Generator().manual_seed(3)
+    h = torch.randn(1, v.latent_dim, 30, generator=g)
+    with torch.no_grad():
+        x = h
+        for blocks in m.upsample:
+            for blk in blocks:
+                x = blk(x)
+        for blk in m.decoder:
+            x = blk(x)
+        hf = x.clamp(-1, 1)[0, 0]
+    mine = OV.Vocoder(v, w).decode_back(h)[0, 0]
+    assert mine.numel() == 30 * 1920 and mine.numel() - hf.numel() == 555
+    tail = 18 * 1920                                              # the last 18 frames: 12 frames away from the left edge
+    assert float((hf[-tail:] - mine[-tail:]).abs().max()) <= 5e-6
+    assert float((hf[:1920] - mine[555:555 + 1920]).abs().max()) > 1e-3    # and the left edge really does differ
