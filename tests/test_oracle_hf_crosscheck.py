@@ -279,3 +279,23 @@ def test_vocoder_back_half_matches_hf_code2wav_stack():
     tail = 18 * 1920                                              # the last 18 frames: 12 frames away from the left edge
     assert float((hf[-tail:] - mine[-tail:]).abs().max()) <= 5e-6
     assert float((hf[:1920] - mine[555:555 + 1920]).abs().max()) > 1e-3    # and the left edge really does differ
+
+
+def test_text_projection_matches_hf_resize_mlp():
+    """TextProjection (talker.rs:294-321): fc1 (bias) -> SiLU -> fc2 (bias), the tensors `talker.text_projection.linear_fc1/2`.
+    transformers' Qwen3-Omni talker has the same module under the same tensor names (`Qwen3OmniMoeTalkerResizeMLP`)."""
+    mm = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    from types import SimpleNamespace
+    spec = S.SPEC_TINY_PROJ
+    w = W.make_talker_weights(spec, dtype=torch.float32)
+    cfg = SimpleNamespace(thinker_hidden_size=spec.text_embed_dim,
+                          text_config=SimpleNamespace(intermediate_size=spec.text_embed_dim, hidden_size=spec.hidden, hidden_act="silu"))
+    m = mm.Qwen3OmniMoeTalkerResizeMLP(cfg).eval()
+    m.load_state_dict({k[len("talker.text_projection."):]: v for k, v in w.items() if k.startswith("talker.text_projection.")}, strict=True)
+    tk = OM.Talker(spec, w, OM.F32P)
+    ids = [3, 77, 1500, 2047]
+    x = w["talker.model.text_embedding.weight"][ids][None]
+    with torch.no_grad():
+        want = m(x)
+    got = tk.projected_text(ids)
+    assert got.shape == want.shape and float((got - want).abs().max()) <= 2e-6 * float(want.abs().max())
