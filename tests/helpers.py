@@ -44,17 +44,37 @@ def bf16_ulp_diff(a: torch.Tensor, b: torch.Tensor):
     return (a - b).abs() / ulp
 
 
-def first_divergence_is_a_near_tie(got, ref, tr):
-    """Returns (match_len, ok): ok is True when the sequences agree, or when the first position where they
-    differ is one where the oracle itself was within the stated margins (see module docstring)."""
+def cdf_window(l2_row, cfg, u, band=0.05):
+    """Tokens whose interval of the oracle's sampling CDF meets [u - band, u + band] (see first_token_window)."""
+    tok, dbg = osmp.sample_row(np.asarray(l2_row, dtype=np.float32), cfg, np.float32(u), return_debug=True)
+    cum = np.cumsum(dbg["probs"].astype(np.float64))
+    lo = np.concatenate([[0.0], cum[:-1]])
+    return int(tok), {int(i) for i in np.nonzero((dbg["probs"] > 0) & (cum >= u - band) & (lo <= u + band))[0]}
+
+
+def first_divergence_is_a_near_tie(got, ref, tr, window_cfg=None):
+    """Returns (match_len, ok, why): ok is True when the sequences agree, or when the first position where they
+    differ is one where the oracle itself was within the stated margins (see test_gpu_model's docstring).
+    With `window_cfg` (the oracle GenerationConfig) a fork at a SAMPLED token is held to the stricter CDF-window rule:
+    the other token must be a neighbour of the oracle's draw (cdf_window), not merely "some boundary within 0.05",
+    which with ~40 survivors is always true (DESIGN.md §5 caveat)."""
     n = min(len(got), len(ref))
     for f in range(n):
         if got[f] == ref[f]:
             continue
         g = next(i for i in range(16) if got[f][i] != ref[f][i])
         if g == 0:       # semantic token = next_tok sampled at the end of frame f-1
-            margin = tr.frames[f - 1]["sample_margin"] if f > 0 else 0.0
-            return f, (f == 0) or margin <= 0.05, ("sample", f, margin)
+            if f == 0:
+                return f, True, ("sample", f, 0.0)
+            fr = tr.frames[f - 1]
+            margin = fr["sample_margin"]
+            if window_cfg is not None:
+                probe = osmp.SamplingContext(0)
+                probe.state = fr["rng_state"]
+                tok, win = cdf_window(fr["penalised"][0], window_cfg, float(probe.rand_f32()))
+                assert tok == ref[f][0], (tok, ref[f][0])           # the trace and the replay agree
+                return f, got[f][0] in win, ("sample-window", f, got[f][0], sorted(win))
+            return f, margin <= 0.05, ("sample", f, margin)
         ol = tr.frames[f]["cp_logits"][g - 1].float()
         top2 = torch.topk(ol, 2).values
         margin = float(top2[0] - top2[1])
@@ -74,9 +94,4 @@ def first_token_window(spec, text_ids, seed, opts, band=0.05, speaker="ryan", la
     vocab = spec.codec_vocab
     l2 = osmp.apply_generation_penalties(logits[:, 0].numpy().astype(np.float32), np.zeros((1, vocab), dtype=np.float32), cfg, 0,
                                          osmp.build_suppression_mask(vocab, 2150))
-    u = float(osmp.SamplingContext(seed).rand_f32())
-    tok, dbg = osmp.sample_row(l2[0], cfg, np.float32(u), return_debug=True)
-    cum = np.cumsum(dbg["probs"].astype(np.float64))
-    lo = np.concatenate([[0.0], cum[:-1]])
-    window = {int(i) for i in np.nonzero((dbg["probs"] > 0) & (cum >= u - band) & (lo <= u + band))[0]}
-    return int(tok), window
+    return cdf_window(l2[0], cfg, float(osmp.SamplingContext(seed).rand_f32()), band)
