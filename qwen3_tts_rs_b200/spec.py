@@ -6,8 +6,8 @@ Mirrors the dimension sources in the reference:
   Decoder12HzConfig::default             (src/models/codec/decoder_12hz.rs:47-67)
   codec / tts special token ids          (src/models/talker.rs:31-54, 96-105, 147-156)
 
-Only dimensions live here; parsing HF config.json stays with the caller
-(SURVEY.md §2 row 10 is out of scope).
+Only dimensions live here; `formats.ParsedModelConfig` turns a checkpoint's config.json
+into one of these tables.
 """
 from __future__ import annotations
 
