@@ -36,15 +36,18 @@ class Trace:
 
     def __init__(self):
         self.frames: List[dict] = []
+        self.first: Optional[dict] = None      # penalised prefill logits + RNG state of the first draw (lib.rs:557-571)
 
 
 def sample_first(talker: Talker, logits: torch.Tensor, cfg: smp.GenerationConfig, ctx: smp.SamplingContext,
-                 penalty_mask: np.ndarray, suppression: np.ndarray, logit_hook=None):
+                 penalty_mask: np.ndarray, suppression: np.ndarray, logit_hook=None, trace: Optional["Trace"] = None):
     """lib.rs:557-571: sample token 0 with token_count = 0."""
     l2 = logits[:, 0].numpy().astype(np.float32)
     if logit_hook is not None:
         l2 = logit_hook(-1, l2)
     l2 = smp.apply_generation_penalties(l2, penalty_mask, cfg, 0, suppression)
+    if trace is not None:
+        trace.first = dict(penalised=l2.copy(), rng_state=ctx.state)
     tok = int(smp.sample(l2, cfg, ctx)[0])
     smp.update_penalty_mask(penalty_mask, tok)
     return tok
@@ -63,7 +66,7 @@ def generate_codes(talker: Talker, cp: CodePredictor, cfg: smp.GenerationConfig,
     penalty_mask = np.zeros((1, vocab), dtype=np.float32)
     cp_caches = cp.new_kv_caches()
 
-    tok = sample_first(talker, initial_logits, cfg, ctx, penalty_mask, suppression, logit_hook)
+    tok = sample_first(talker, initial_logits, cfg, ctx, penalty_mask, suppression, logit_hook, trace)
     token_count = 1
     frames: List[List[int]] = []
     for frame_idx in range(cfg.max_new_tokens):
@@ -120,6 +123,74 @@ def prefill_and_generate(talker: Talker, cp: CodePredictor, prefill_embeds: torc
     last_hidden = hidden[:, plen - 1: plen]
     return generate_codes(talker, cp, cfg, ctx, caches, plen, last_hidden, logits, trailing, tlen, pad,
                           trace=trace, logit_hook=logit_hook)
+
+
+def follow(talker: Talker, cp: CodePredictor, prefill_embeds: torch.Tensor, text_ids: Sequence[int],
+           cfg: smp.GenerationConfig, seed: int, frames: Sequence[Sequence[int]],
+           first_logits: Optional[np.ndarray] = None, frame_logits: Optional[Sequence[np.ndarray]] = None,
+           kv_max: Optional[int] = None) -> dict:
+    """Test aid (no reference counterpart): the loop of generate_codes (lib.rs:530-656) FOLLOWING a trajectory produced
+    elsewhere.  `frames[f] = [tok, c0..c14]` are the codes the CUDA path emitted; every decision input (semantic token,
+    acoustic codes fed to the next code-predictor pass, penalty mask) is taken from them, every tensor is this oracle's
+    own.  Returns per frame the oracle's code-predictor logits, its own arg-max codes, the talker input built from the
+    followed codes (lib.rs:612-622), the talker hidden state and raw logits -- so the other side can be compared
+    element-wise at EVERY frame of a free-running run, not only up to its first near-tie fork.
+
+    Sampler replay: when `first_logits` ([V] f32, the prefill logits the other side sampled token 0 from) and
+    `frame_logits[f]` ([V] f32, the talker logits it sampled frame f+1's token from) are given, the oracle's penalty /
+    top-k / top-p / multinomial pipeline (sampling.rs:140-319, lib.rs:1271-1322) is run on THOSE logits with this
+    oracle's RNG stream and penalty mask; `replayed[f]` is the token it draws (index 0 = the first token), `margins[f]`
+    the draw's distance from the nearest CDF boundary and `rng_states[f]` the PCG state before the draw."""
+    p: Prec = talker.p
+    vocab = talker.spec.codec_vocab
+    suppression = smp.build_suppression_mask(vocab, 2150)
+    penalty_mask = np.zeros((1, vocab), dtype=np.float32)
+    ctx = smp.SamplingContext(seed)
+    trailing, tlen, pad = talker.build_trailing_text(text_ids)
+    caches = talker.new_kv_caches(kv_max if kv_max is not None else cfg.max_new_tokens + 256)
+    hidden, logits = talker.run_prefill_layers(prefill_embeds, caches)
+    offset = hidden.shape[1]
+    last_hidden = hidden[:, offset - 1: offset]
+    cp_caches = cp.new_kv_caches()
+    out = dict(prefill_logits=logits[:, 0].numpy().astype(np.float32)[0], frames=[], replayed=[], margins=[], rng_states=[])
+
+    def replay(raw, token_count):
+        l2 = smp.apply_generation_penalties(np.asarray(raw, dtype=np.float32)[None], penalty_mask, cfg, token_count, suppression)
+        out["rng_states"].append(ctx.state)
+        probe = smp.SamplingContext(0)
+        probe.state = ctx.state
+        tok = int(smp.sample(l2, cfg, ctx)[0])
+        margin = None
+        if cfg.temperature >= 0.01:
+            _, dbg = smp.sample_row(l2[0], cfg, probe.rand_f32(), return_debug=True)
+            margin = dbg["margin"]
+        out["replayed"].append(tok)
+        out["margins"].append(margin)
+
+    if first_logits is not None or frame_logits is not None:
+        replay(first_logits if first_logits is not None else out["prefill_logits"], 0)    # one draw per sampled token
+    if len(frames):
+        smp.update_penalty_mask(penalty_mask, int(frames[0][0]))
+    token_count = 1
+    for f, fr in enumerate(frames):
+        tok, forced = int(fr[0]), [int(c) for c in fr[1:]]
+        sem = talker.codec_embed([tok])
+        own_codes, cp_logits = cp.generate_acoustic_codes(last_hidden, sem, cp_caches, return_logits=True, forced_codes=forced)
+        summed = p.r(sem + cp.acoustic_embeddings_sum(forced))                 # lib.rs:612-615
+        text_add = trailing[:, f: f + 1] if f < tlen else pad                  # lib.rs:617-621
+        step_input = p.r(summed + text_add)
+        h, lg = talker.generate_step_with_embed(step_input, caches, offset)
+        offset += 1
+        out["frames"].append(dict(frame=f, cp_logits=cp_logits, own_codes=own_codes, step_input=step_input.clone(),
+                                  hidden=h.clone(), logits=lg[:, 0].numpy().astype(np.float32)[0]))
+        if frame_logits is not None:
+            replay(frame_logits[f], token_count)
+        nxt = int(frames[f + 1][0]) if f + 1 < len(frames) else (out["replayed"][-1] if frame_logits is not None else None)
+        if nxt is not None:
+            smp.update_penalty_mask(penalty_mask, nxt)
+        token_count += 1
+        last_hidden = h
+    return out
 
 
 class StreamingSession:

@@ -351,8 +351,13 @@ class CodePredictor:
             h = decoder_layer(self.p, lw, h, cos, sin, mask, c, sp.cp_heads, sp.cp_kv_heads, sp.head_dim, sp.rms_eps)
         return rms_norm(self.p, h, self.norm, sp.rms_eps)
 
-    def generate_acoustic_codes(self, talker_hidden, semantic_embed, caches, return_logits: bool = False):
-        """code_predictor.rs:320-416: greedy argmax for each of the 15 codebooks."""
+    def generate_acoustic_codes(self, talker_hidden, semantic_embed, caches, return_logits: bool = False,
+                                forced_codes: Optional[Sequence[int]] = None):
+        """code_predictor.rs:320-416: greedy argmax for each of the 15 codebooks.
+        `forced_codes` (test aid, no reference counterpart): the embedding fed to pass g+1 is that of forced_codes[g]
+        instead of this pass's own arg-max, so the oracle can FOLLOW a trajectory produced elsewhere (the CUDA path) and
+        its per-pass logits stay comparable after the other side took a near-tie the other way.  The returned codes are
+        still this oracle's own arg-max of every pass."""
         for c in caches:
             c.reset()
         n_ac = self.spec.groups - 1
@@ -363,7 +368,8 @@ class CodePredictor:
         codes = [int(torch.argmax(logits.flatten()))]
         offset = 2
         for g in range(1, n_ac):
-            e = self.codec_embeddings[g - 1][codes[-1]][None, None]
+            prev = codes[-1] if forced_codes is None else int(forced_codes[g - 1])
+            e = self.codec_embeddings[g - 1][prev][None, None]
             h = self._layers(self._project(e), caches, offset, None)
             logits = linear(self.p, h, self.lm_heads[g])
             all_logits.append(logits)

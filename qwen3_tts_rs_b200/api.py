@@ -239,6 +239,26 @@ class Session:
         L.check(self.lib.q3_generate(self.handle, max_frames, _ptr(codes), _ptr(n)))
         return codes, n
 
+    def generate_tapped(self, max_frames: int):
+        """q3_debug_generate_tapped (test aid): q3_generate with the loop's decision inputs read back every frame.
+        Returns (codes, n_frames, taps) with taps = dict(first_logits [B,V], logits [F,B,V], cp_logits [F,15,B,cpV],
+        rng [F+2,B] (PCG state before the first draw, then after every draw), step_input bf16 [F,B,H])."""
+        sp = self.model.spec
+        B, F, n_ac = self.B, max_frames, sp.groups - 1
+        codes = np.zeros((B, F, 16), dtype=np.uint32)
+        n = np.zeros(B, dtype=np.int32)
+        taps = dict(first_logits=np.zeros((B, sp.codec_vocab), dtype=np.float32),
+                    logits=np.zeros((F, B, sp.codec_vocab), dtype=np.float32),
+                    cp_logits=np.zeros((F, n_ac, B, sp.cp_vocab), dtype=np.float32),
+                    rng=np.zeros((F + 2, B), dtype=np.uint64),
+                    step_input=torch.zeros(F, B, sp.hidden, dtype=torch.bfloat16))
+        fn = self.lib.q3_debug_generate_tapped
+        fn.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 7
+        fn.restype = C.c_int
+        L.check(fn(self.handle, F, _ptr(codes), _ptr(n), _ptr(taps["first_logits"]), _ptr(taps["logits"]),
+                   _ptr(taps["cp_logits"]), _ptr(taps["rng"]), _ptr(taps["step_input"])))
+        return codes, n, taps
+
     def generate_async(self, max_frames: int):
         L.check(self.lib.q3_generate_async(self.handle, max_frames))
 

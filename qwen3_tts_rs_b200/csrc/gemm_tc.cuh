@@ -16,6 +16,7 @@
 // Out-of-range tokens are zero-filled by TMA; N must be a multiple of 128 and K of 64 (true for every Qwen3-TTS
 // projection), otherwise the caller uses the CUDA-core GEMV.
 #pragma once
+#include <mutex>
 #include <cuda.h>
 
 #include "common.cuh"
@@ -238,12 +239,20 @@ static void gemm_tc_launch(const bf16* W, const bf16* W2, const bf16* X, int ldx
   CUtensorMap tw2 = dual ? make_tmap_2d(W2, a.N, a.K, a.K) : tw;
   CUtensorMap tx = make_tmap_2d(X, a.T, a.K, ldx);
   dim3 grid(a.N / TC_BM_, ceil_div(a.T, TC_BN_));
-  static bool configured = false;
   const size_t smem_single = 4 * 2 * TC_TILE_BYTES + 1024, smem_dual = 3 * 3 * TC_TILE_BYTES + 1024;
-  if (!configured) {
-    Q3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_single));
-    Q3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dual));
-    configured = true;
+  {
+    // the shared-memory opt-in is a per-DEVICE function attribute: one process may hold models on several GPUs
+    // (q3_model_desc.device) and sessions launch from several threads
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    Q3_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      Q3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_single));
+      Q3_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dual));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
   }
   if (dual) gemm_tc_kernel<true><<<grid, 128, smem_dual, st>>>(tw, tw2, tx, a);
   else gemm_tc_kernel<false><<<grid, 128, smem_single, st>>>(tw, tw2, tx, a);

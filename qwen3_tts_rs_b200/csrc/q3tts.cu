@@ -64,6 +64,7 @@ struct q3_session {
   int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
   size_t m2_smem = 0, m3_smem = 0;
   DBuf prof;                       // optional timestamp buffer (q3_debug_profile)
+  float* tap_cp_logits = nullptr;  // q3_debug_generate_tapped: device [15][B][cp_vocab] written by every frame's CP heads
   size_t mega_smem = 0;
   int mega_grid = 0;
   DBuf bar, ss;
@@ -339,7 +340,7 @@ static void cp_frame(q3_session* s, float* logits_out /* [15][B][cp_vocab] or nu
 static void frame_body(q3_session* s) {
   const q3_model* m = s->m;
   const q3_model_desc& d = m->d;
-  cp_frame(s, nullptr);
+  cp_frame(s, s->tap_cp_logits);
   EmbTable tab{};
   for (int i = 0; i < d.groups - 1; ++i) tab.e[i] = m->cp_emb[i];
   frame_finish_kernel<<<s->B, 256, 0, s->st>>>(s->fs, tab, m->codec_emb, s->step_input.as<bf16>(), d.hidden, s->B,
@@ -507,7 +508,13 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
         h.X = g == 0 ? (const void*)(reinterpret_cast<const char*>(xT) + (size_t)C * 4) : (const void*)xT;
         h.ldx = g == 0 ? 2 * C : C;
         h.epi = EPI_LOGITS; h.amax = amax_g + (size_t)g * B + row0;
-        h.Yf = cp_logits ? cp_logits + ((size_t)g * B + row0) * d.cp_vocab : nullptr;
+        {
+          // one-off programs pass their own buffer ([15][B] rows, r0 == 0); the full-frame program of a tapped run writes
+          // into the session's tap buffer, whose leading dimension is the whole batch
+          float* lg = cp_logits ? cp_logits : s->tap_cp_logits;
+          const int ldb = cp_logits ? B : Btot;
+          h.Yf = lg ? lg + ((size_t)g * ldb + (cp_logits ? 0 : r0) + row0) * d.cp_vocab : nullptr;
+        }
         pick_small(h); pr.push_back(h);
       }
     }
@@ -1016,6 +1023,15 @@ static void reset_state(q3_session* s, const uint64_t* seeds) {
   s->prefilled = false;
   s->first_sampled = false;
   s->frames_run = 0;
+  if (s->m2_tag.p) {
+    // Tags are a 32-bit counter that only ever grows inside a session (one per phase, ~550 per frame): a reused session
+    // would wrap it after ~7.8 M frames.  A reset is a quiescent point (the stream was just synchronised), so restart the
+    // counter here and clear the tagged buffers, whose stale tags could otherwise alias the restarted sequence.
+    const unsigned one = 1;
+    Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_tag.p, &one, 4, cudaMemcpyHostToDevice, s->st));
+    s->m2_x.zero(s->st); s->m2_qkv.zero(s->st); s->m2_attn.zero(s->st); s->m2_h1.zero(s->st); s->m2_act.zero(s->st);
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  }
   std::fill(s->prefill_len.begin(), s->prefill_len.end(), 0);
   std::fill(s->stream_emitted.begin(), s->stream_emitted.end(), 0);
 }
@@ -1457,6 +1473,24 @@ q3_status q3_vocoder_decode(const q3_model* m, const int64_t* codes, int32_t bat
   Q3_REQUIRE(m && codes && pcm && batch >= 0 && t >= 0, Q3_ERR_INVALID, "bad argument");
   Q3_REQUIRE(m->finalized && m->has_vocoder, Q3_ERR_STATE, "model has no finalized vocoder weights");
   if (batch == 0 || t == 0) return Q3_OK;       // codes_to_tensor of zero frames -> empty waveform
+  {
+    // the reference's index_select fails on an out-of-range code (decoder_12hz.rs:429, 443): a caller bug must not become
+    // plausible-sounding audio.  Semantic codes are reduced modulo the codebook size (decoder_12hz.rs:423-427), so only a
+    // negative one is an error there (Rust's % keeps the sign and index_select then fails).
+    const int nq = m->d.v_quantizers;
+    const int64_t cb = m->d.v_codebook_size;
+    for (int b = 0; b < batch; ++b)
+      for (int q = 0; q < nq; ++q) {
+        const int64_t* row = codes + ((size_t)b * nq + q) * t;
+        for (int f = 0; f < t; ++f) {
+          const int64_t c = row[f];
+          if (c < 0 || (q > 0 && c >= cb))
+            throw Q3Error(Q3_ERR_INVALID, "code out of range: batch " + std::to_string(b) + " quantizer " + std::to_string(q) +
+                                              " frame " + std::to_string(f) + " value " + std::to_string((long long)c) +
+                                              " (codebook size " + std::to_string((long long)cb) + ")");
+        }
+      }
+  }
   Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
   std::lock_guard<std::mutex> lock(m->voc_mutex);
   const int up = vocoder_total_upsample(m);
@@ -1600,6 +1634,62 @@ q3_status q3_fused_residual_rmsnorm_host(const void* x, const void* r, const voi
   Q3_CHECK_CUDA(cudaDeviceSynchronize());
   Q3_CHECK_CUDA(cudaMemcpy(out_normed, dn.p, n, cudaMemcpyDeviceToHost));
   Q3_CHECK_CUDA(cudaMemcpy(out_sum, dsum.p, n, cudaMemcpyDeviceToHost));
+  Q3_API_END
+}
+
+// Test aid (not part of the drop-in boundary): q3_generate with the loop's decision inputs tapped every frame, so a test can
+// replay the reference's sampler on the very logits this path sampled from and compare every tensor of a FREE-RUNNING run
+// with an oracle that follows the emitted codes (oracle/generate.py follow()).  Same kernels and phase program as
+// q3_generate; frames run one per launch so that the taps can be read back between them (the codes are bit-identical to
+// an untapped run -- tests/test_gpu_parity.py asserts it).  Host buffers, any of them may be NULL:
+//   first_logits f32 [B][V]            prefill logits token 0 is sampled from (lib.rs:557-571)
+//   logits       f32 [F][B][V]         raw talker logits of frame f (lib.rs:627-631), before penalties
+//   cp_logits    f32 [F][15][B][cpV]   code-predictor logits of every pass (code_predictor.rs:357-413)
+//   rng          u64 [F+2][B]          PCG state before the first draw, then after every draw
+//   step_input   bf16 [F][B][H]        talker input of frame f (lib.rs:612-622)
+q3_status q3_debug_generate_tapped(q3_session* s, int32_t max_frames, uint32_t* codes, int32_t* n_frames, float* first_logits,
+                                   float* logits, float* cp_logits, uint64_t* rng, uint16_t* step_input) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && codes && n_frames && max_frames >= 0, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(s->prefilled && !s->first_sampled, Q3_ERR_STATE, "tapped generation needs a freshly prefilled session");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  const size_t B = s->B, V = d.codec_vocab, cpV = d.cp_vocab, H = d.hidden, n_ac = d.groups - 1;
+  if (cp_logits) {
+    s->cp_logits.ensure(n_ac * B * cpV * 4);
+    s->tap_cp_logits = s->cp_logits.as<float>();
+    s->m2_n_ph = 0;                 // the cached frame program does not write logits: rebuild with the tap
+    invalidate_graph(s);
+  }
+  struct Untap {
+    q3_session* s;
+    ~Untap() { if (s->tap_cp_logits) { s->tap_cp_logits = nullptr; s->m2_n_ph = 0; invalidate_graph(s); } }
+  } untap{s};
+  if (first_logits) Q3_CHECK_CUDA(cudaMemcpyAsync(first_logits, s->logits.p, B * V * 4, cudaMemcpyDeviceToHost, s->st));
+  if (rng) Q3_CHECK_CUDA(cudaMemcpyAsync(rng, s->rng.p, B * 8, cudaMemcpyDeviceToHost, s->st));
+  sample_first_if_needed(s);
+  if (rng) Q3_CHECK_CUDA(cudaMemcpyAsync(rng + B, s->rng.p, B * 8, cudaMemcpyDeviceToHost, s->st));
+  const int budget = frames_budget(s, max_frames);
+  std::vector<int> dn(B);
+  for (int f = 0; f < budget; ++f) {
+    Q3_CHECK_CUDA(cudaMemcpyAsync(dn.data(), s->done.p, B * 4, cudaMemcpyDeviceToHost, s->st));
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+    bool all_done = true;
+    for (size_t b = 0; b < B; ++b) all_done = all_done && dn[b] != 0;
+    if (all_done) break;
+    run_frames(s, 1);
+    if (logits) Q3_CHECK_CUDA(cudaMemcpyAsync(logits + (size_t)f * B * V, s->logits.p, B * V * 4, cudaMemcpyDeviceToHost, s->st));
+    if (cp_logits)
+      Q3_CHECK_CUDA(cudaMemcpyAsync(cp_logits + (size_t)f * n_ac * B * cpV, s->cp_logits.p, n_ac * B * cpV * 4, cudaMemcpyDeviceToHost, s->st));
+    if (rng) Q3_CHECK_CUDA(cudaMemcpyAsync(rng + (size_t)(f + 2) * B, s->rng.p, B * 8, cudaMemcpyDeviceToHost, s->st));
+    if (step_input)
+      Q3_CHECK_CUDA(cudaMemcpyAsync(step_input + (size_t)f * B * H, s->step_input.p, B * H * 2, cudaMemcpyDeviceToHost, s->st));
+  }
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  mega2_check_watchdog(s);
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
+  Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
+  return q3_get_codes(s, max_frames, codes, n_frames);
   Q3_API_END
 }
 

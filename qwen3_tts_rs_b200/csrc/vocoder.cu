@@ -96,11 +96,18 @@ bool use_mma_path() {
 }
 
 void launch_mma(MmaConvArgs& a, int grid_q, int Cout_pad, int z, cudaStream_t st) {
-  static bool configured = false;
   const size_t smem = mma_conv_smem_bytes(a.max_shift - a.min_shift);
-  if (!configured) {
-    Q3_CHECK_CUDA(cudaFuncSetAttribute(voc_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    configured = true;
+  {
+    // per-DEVICE function attribute (see gemm_tc_launch)
+    static std::mutex mu;
+    static bool configured[64] = {};
+    int dev = 0;
+    Q3_CHECK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      Q3_CHECK_CUDA(cudaFuncSetAttribute(voc_conv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
   }
   Q3_REQUIRE(smem <= 100 * 1024, Q3_ERR_UNSUPPORTED, "conv window too large for the staged tile");
   Q3_REQUIRE((MC_BK / 2) * (MC_BN + a.max_shift - a.min_shift) <= 12 * 256, Q3_ERR_UNSUPPORTED,

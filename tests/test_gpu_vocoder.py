@@ -80,10 +80,27 @@ def test_decode_codes_empty_and_layout():
     assert len(audio) == 1920 and audio.sample_rate == 24000
 
 
+def test_out_of_range_codes_are_an_error():
+    """decoder_12hz.rs:429, 443: index_select fails on an acoustic code >= codebook_size or a negative code; semantic codes
+    are reduced modulo the codebook size (decoder_12hz.rs:423-427), so 3071 is fine there."""
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    codes = _rand_codes(1, 4, 1)
+    codes[0, 0, 2] = 3071
+    assert tts.decode_tensor(codes).shape == (1, 4 * 1920)
+    for q, f, v in ((3, 1, 2048), (15, 0, -1), (0, 3, -5)):
+        bad = codes.copy()
+        bad[0, q, f] = v
+        with pytest.raises(api.L.Q3Error) as e:
+            tts.decode_tensor(bad)
+        assert e.value.status == "Q3_ERR_INVALID" and "out of range" in str(e.value)
+
+
 def test_streaming_session_matches_oracle_chunks():
-    """StreamingSession (lib.rs:1650-1759): chunk_frames = 4, 10 frames -> chunks of 4,4,2 frames, each
-    vocoded independently; codes equal the non-streaming run; per-chunk PCM within tolerance of the oracle's
-    per-chunk decode; total samples == frames * 1920 (streaming_e2e.rs:150-157)."""
+    """StreamingSession (lib.rs:1650-1759): chunk_frames = 4, 10 frames -> chunks of 4,4,2 frames, each vocoded
+    independently.  Held unconditionally: the streamed codes equal the non-streamed run's codes value for value; every
+    chunk's PCM equals (rms <= 1e-3) the oracle vocoder's decode of THAT chunk's codes alone (no state crosses chunks,
+    lib.rs:1755-1758); chunk sizes equal the oracle session's; total samples == frames * 1920 (streaming_e2e.rs:150-157)."""
     spec = S.SPEC_TINY
     vw = vocoder_weights(spec.vocoder, "tiny")
     tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
@@ -94,16 +111,30 @@ def test_streaming_session_matches_oracle_chunks():
     emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
     osess = OG.StreamingSession(tk, cp, lambda c: voc.decode(c)[0, 0].numpy(), emb, ids, oracle_cfg(opts), 99, chunk_frames=4)
     ochunks = list(osess)
+    # the API object (chunk sizes, done flag, frame count) ...
     sess = tts.synthesize_streaming(ids, options=opts)
     chunks = list(sess)
     assert sess.is_done()
-    assert [len(c) for c in chunks] == [len(c) for c in ochunks]
+    assert [len(c) for c in chunks] == [len(c) for c in ochunks] == [4 * 1920, 4 * 1920, 2 * 1920]
     assert sum(len(c) for c in chunks) == sess.frames_generated() * 1920
+    # ... and the same stream through the session call that also returns each chunk's codes
+    prompts = [tts.custom_voice_prompt(ids, "ryan", "english")]
+    low = tts._new_session([ids], prompts, opts, [99])
+    streamed, pcm_chunks = [], []
+    while True:
+        codes, pcm, n, done = low.stream_next()
+        if n[0]:
+            streamed.append(codes[0, : n[0]].tolist())
+            pcm_chunks.append(pcm[0, : n[0] * 1920].copy())
+        if done:
+            break
+    low.close()
     nonstream = tts.generate_codes([ids], options=opts, seeds=[99])[0]
-    assert len(nonstream) == sess.frames_generated()
-    if nonstream == osess.all_frames:      # identical codes -> PCM comparable chunk by chunk
-        for i, (c, o) in enumerate(zip(chunks, ochunks)):
-            _check(c.samples, o, f"chunk {i}")
+    assert [f for ch in streamed for f in ch] == nonstream                 # streamed codes == non-streamed codes
+    assert len(pcm_chunks) == len(chunks)
+    for i, (ch, p, c) in enumerate(zip(streamed, pcm_chunks, chunks)):
+        assert np.array_equal(p, c.samples)                                # both stream calls give the same samples
+        _check(p, voc.decode(OG.codes_to_tensor(ch))[0, 0].numpy(), f"chunk {i}")
 
 
 def test_synthesize_with_voice_end_to_end():

@@ -312,8 +312,8 @@ def test_vocoder_back_half_receptive_field():
 
 def test_fork_rules_of_the_gpu_parity_tests():
     """The exemption rules the GPU tests apply to a free-running fork (tests/helpers.py), exercised on the oracle's own trace
-    with hand-made forks: an arg-max fork passes only at a near-tie; a sampled fork passes the old nearest-boundary rule
-    almost always (that rule is weak) but passes the CDF-window rule only for a neighbour of the draw."""
+    with hand-made forks: an arg-max fork passes only at a near-tie; a sampled fork (the first token included) passes the
+    CDF-window rule only for a neighbour of the draw."""
     from helpers import cdf_window, first_divergence_is_a_near_tie, oracle_cfg, oracle_run
     from qwen3_tts_rs_b200 import api
     spec = S.SPEC_TINY
@@ -321,7 +321,7 @@ def test_fork_rules_of_the_gpu_parity_tests():
     ids = W.synthetic_prompt(1, spec)
     ref, tr, _ = oracle_run(spec, ids, 11, opts, trace=True)
     cfg = oracle_cfg(opts)
-    assert first_divergence_is_a_near_tie(ref, ref, tr, window_cfg=cfg)[:2] == (len(ref), True)
+    assert first_divergence_is_a_near_tie(ref, ref, tr, cfg)[:2] == (len(ref), True)
     # sampled fork at frame 3: to a CDF neighbour, and to a token far from the draw
     fr = tr.frames[2]
     probe = osmp.SamplingContext(0)
@@ -333,12 +333,19 @@ def test_fork_rules_of_the_gpu_parity_tests():
     for other, want in ((neighbour, True), (far, False)):
         got = [list(f) for f in ref]
         got[3][0] = other
-        m, ok, why = first_divergence_is_a_near_tie(got, ref, tr, window_cfg=cfg)
+        m, ok, why = first_divergence_is_a_near_tie(got, ref, tr, cfg)
         assert (m, ok) == (3, want), why
-        assert first_divergence_is_a_near_tie(got, ref, tr)[1] is True      # the old rule cannot tell them apart
+    # the same at the FIRST token (sampled from the prefill logits): only a neighbour passes
+    probe.state = tr.first["rng_state"]
+    tok0, win0 = cdf_window(tr.first["penalised"][0], cfg, float(probe.rand_f32()))
+    assert tok0 == ref[0][0]
+    far0 = next(t for t in range(2048) if t not in win0)
+    got = [list(f) for f in ref]
+    got[0][0] = far0
+    assert first_divergence_is_a_near_tie(got, ref, tr, cfg)[:2] == (0, False)
     # arg-max fork at a code whose top-2 margin is wide: refused by both rules
     got = [list(f) for f in ref]
     g = max(range(15), key=lambda i: float(torch.topk(tr.frames[1]["cp_logits"][i].float(), 2).values.diff().abs()))
     got[1][g + 1] = (ref[1][g + 1] + 1) % 2048
-    assert first_divergence_is_a_near_tie(got, ref, tr, window_cfg=cfg)[:2] == (1, False)
-    assert first_divergence_is_a_near_tie(ref[:4], ref, tr)[1] is False       # a length mismatch is not a fork
+    assert first_divergence_is_a_near_tie(got, ref, tr, cfg)[:2] == (1, False)
+    assert first_divergence_is_a_near_tie(ref[:4], ref, tr, cfg)[1] is False       # a length mismatch is not a fork

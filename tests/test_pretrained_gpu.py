@@ -86,7 +86,7 @@ def test_ragged_and_degenerate_prompts_in_one_batch():
     talker.rs:479-487 / lib.rs:509-516), a single text token (10 positions, trailing = tts_eos), an ordinary prompt and a
     two-token one; rows of different prefill lengths are right-padded inside q3_prefill_ids.  Every row, in the batch and
     run alone, must equal an independent oracle run up to the near-tie rule of test_gpu_model.py."""
-    from helpers import first_divergence_is_a_near_tie, first_token_window, gpu_tts, oracle_run
+    from helpers import first_divergence_is_a_near_tie, first_token_window, gpu_tts, oracle_cfg, oracle_run
     spec = S.SPEC_TINY
     tts = gpu_tts(spec)
     prompts = [[], [7], W.synthetic_prompt(4, spec), [11, 12]]
@@ -101,10 +101,10 @@ def test_ragged_and_degenerate_prompts_in_one_batch():
         assert tok0 == ref[0][0] and tok0 in window and len(window) <= 12
         # the first token depends on the prefill only: the oracle's token, or a CDF neighbour within 0.05 of the draw
         assert got[b][0][0] in window, (b, got[b][0], ref[0], sorted(window))
-        m, ok, why = first_divergence_is_a_near_tie(got[b], ref, tr)
+        m, ok, why = first_divergence_is_a_near_tie(got[b], ref, tr, oracle_cfg(opts))
         report.append((b, m, ok, why))
         solo = tts.generate_codes([ids], options=opts, seeds=[seeds[b]])[0]
-        m2, ok2, why2 = first_divergence_is_a_near_tie(solo, ref, tr)
+        m2, ok2, why2 = first_divergence_is_a_near_tie(solo, ref, tr, oracle_cfg(opts))
         assert ok2 and solo[0][0] in window, (b, m2, why2)
         report.append((b, "solo == batch row", solo == got[b]))
     print("ragged batch (row, match_len, fork_is_near_tie, detail):", report)
