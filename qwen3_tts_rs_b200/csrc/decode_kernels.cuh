@@ -315,7 +315,18 @@ __global__ void cp_embed_kernel(FrameState st, const bf16* __restrict__ emb_g, b
 //   acc = E0[a0]; acc = bf16(acc + Ei[ai]) (i = 1..14, in order); summed = bf16(sem + acc);
 //   step_input = bf16(summed + (frame_idx < lt ? trailing[frame_idx] : tts_pad)).
 struct EmbTable { const bf16* e[15]; };
+// How the threads that execute a row body synchronise: the whole block (stand-alone kernels, mega.cuh / mega2.cuh), or
+// the 512 compute threads of a warp-specialised kernel whose producer warp does not take part (mega4.cuh).
+struct SyncBlock {
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+  static __device__ __forceinline__ int threads() { return blockDim.x; }
+};
+struct SyncCompute512 {
+  static __device__ __forceinline__ void sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+  static __device__ __forceinline__ int threads() { return 512; }
+};
 // body for one row b, executed by a whole block; codes_sm: 16 x u32 of shared memory
+template <typename SY = SyncBlock>
 __device__ __forceinline__ void frame_finish_row(const FrameState& st, const EmbTable& tab, const bf16* __restrict__ codec_emb,
                                                  bf16* __restrict__ step_input, int H, int B, int n_ac, int b,
                                                  uint32_t* codes_sm) {
@@ -326,14 +337,14 @@ __device__ __forceinline__ void frame_finish_row(const FrameState& st, const Emb
     else c = argmax_key_index(__ldcg(st.amax + (size_t)(n_ac - 1) * B + b));
     codes_sm[threadIdx.x] = c;
   }
-  __syncthreads();
+  SY::sync();
   const int fi = st.frame_idx[b];
   const bool active = !st.done[b];
   if (active && threadIdx.x < 16 && fi < st.frames_cap)
     st.codes[((size_t)b * st.frames_cap + fi) * 16 + threadIdx.x] = codes_sm[threadIdx.x];
   if (active && threadIdx.x == 0) st.n_frames[b] = fi + 1;
   const bf16* text = (fi < st.lt[b]) ? st.trailing + ((size_t)b * st.lt_max + fi) * H : st.tts_pad;
-  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) {
+  for (int c = threadIdx.x * 8; c < H; c += SY::threads() * 8) {
     float acc[8], f[8];
     unpack8(*reinterpret_cast<const uint4*>(tab.e[0] + (size_t)codes_sm[1] * H + c), acc);
     for (int i = 1; i < n_ac; ++i) {
@@ -349,7 +360,7 @@ __device__ __forceinline__ void frame_finish_row(const FrameState& st, const Emb
     for (int e = 0; e < 8; ++e) acc[e] = rbf(acc[e] + f[e]);
     *reinterpret_cast<uint4*>(step_input + (size_t)b * H + c) = pack8(acc);
   }
-  __syncthreads();
+  SY::sync();
 }
 
 __global__ void frame_finish_kernel(FrameState st, EmbTable tab, const bf16* __restrict__ codec_emb,
@@ -435,6 +446,7 @@ struct SampleSmem {
 };
 
 // One row, executed by a whole block of any size that is a multiple of 32.
+template <typename SY = SyncBlock>
 __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b, SampleSmem& sm) {
   float* xs = sm.xs;
   float* srt = sm.srt;
@@ -444,7 +456,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
   float& s_mx = sm.s_mx;
   int& s_nkept = sm.s_nkept;
   int& s_tok = sm.s_tok;
-  const int tid = threadIdx.x, V = a.V, NT = blockDim.x;
+  const int tid = threadIdx.x, V = a.V, NT = SY::threads();
   const float* lg = a.logits + (size_t)b * V;
   uint8_t* seen = a.seen + (size_t)b * V;
   const int tcount = a.token_count ? a.token_count[b] : a.token_count_imm;
@@ -460,7 +472,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
     xs[i] = x;
     srt[i] = x;
   }
-  __syncthreads();
+  SY::sync();
   if (a.greedy) {                                                                 // sampling.rs:155-157
     // arg-max, lowest index among ties
     unsigned long long best = 0ull;
@@ -475,12 +487,12 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
       best = other > best ? other : best;
     }
     if ((tid & 31) == 0) red[tid >> 5] = best;
-    __syncthreads();
+    SY::sync();
     if (tid == 0) {
       for (int w = 1; w < (NT >> 5); ++w) best = red[w] > best ? red[w] : best;
       s_tok = (int)argmax_key_index(best);
     }
-    __syncthreads();
+    SY::sync();
   } else {
     // bitonic sort, descending, 4096 keys / 1024 threads
     for (int k = 2; k <= 4096; k <<= 1) {
@@ -493,7 +505,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
             if (desc ? (x < y) : (x > y)) { srt[i] = y; srt[ixj] = x; }
           }
         }
-        __syncthreads();
+        SY::sync();
       }
     }
     if (tid == 0) {
@@ -522,7 +534,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
       s_thr = thr;
       s_mx = srt[0];
     }
-    __syncthreads();
+    SY::sync();
     // compact survivors (x >= thr) in index order; one warp, ballot + popc
     if (tid < 32) {
       const float thr = s_thr, mx = s_mx;
@@ -540,7 +552,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
       }
       if (tid == 0) s_nkept = n;
     }
-    __syncthreads();
+    SY::sync();
     if (tid == 0) {
       const int n = s_nkept;
       float sum = 0.f;
@@ -568,7 +580,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
       if (!found) tok = 0;
       s_tok = tok;
     }
-    __syncthreads();
+    SY::sync();
   }
   if (tid == 0) {
     const int tok = s_tok;

@@ -78,6 +78,8 @@ struct M2Args {
   int bench_barriers;
   int ring_shift;       // ring kernel: log2 of the number of ring stages in use (<= 3)
   int pf_sleep;         // ring kernel: nanoseconds the producer warp sleeps between polls of a full ring
+  int m4_slots;         // mega4.cuh: ring slots in use
+  int m4_red2;          // mega4.cuh: the combine buffer is double-buffered over tiles
 };
 
 // ---------------------------------------------------------------------------------------------------

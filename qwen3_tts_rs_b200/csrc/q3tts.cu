@@ -13,6 +13,7 @@
 #include "mega.cuh"
 #include "mega2.cuh"
 #include "mega3.cuh"
+#include "mega4.cuh"
 #include "model.h"
 
 std::atomic<uint64_t> g_q3_launches{0};
@@ -62,7 +63,8 @@ struct q3_session {
   std::vector<DBuf> m2_progs;      // cached full-frame program of every row group
   std::vector<int> m2_group_nph;
   int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
-  size_t m2_smem = 0, m3_smem = 0;
+  size_t m2_smem = 0, m3_smem = 0, m4_smem = 0;
+  int m4_slots = 0, m4_red2 = 0;
   DBuf prof;                       // optional timestamp buffer (q3_debug_profile)
   float* tap_cp_logits = nullptr;  // q3_debug_generate_tapped: device [15][B][cp_vocab] written by every frame's CP heads
   size_t mega_smem = 0;
@@ -601,6 +603,7 @@ static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   a.pf_sleep = e3 ? std::atoi(e3) : 200;
   const char* e4 = std::getenv("Q3_RING_SHIFT");
   a.ring_shift = e4 ? std::min(3, std::max(0, std::atoi(e4))) : 3;
+  a.m4_slots = s->m4_slots; a.m4_red2 = s->m4_red2;
   return a;
 }
 
@@ -625,7 +628,10 @@ static void mega2_launch(q3_session* s, M2Args& a, const DBuf& prog, int n_ph, b
     if (a.prof_mode == 2 && (size_t)a.prof_cap < (size_t)(n_ph * 4 + 8) * s->mega_grid + 2048) a.prof_mode = 0;
   }
   void* params[] = {(void*)&a};
-  if (s->mega_ver == 3 && !force_v2)
+  if (s->mega_ver == 4 && !force_v2)
+    Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega4_kernel, dim3(s->mega_grid), dim3(M4_THREADS), params,
+                                              s->m4_smem, s->st));
+  else if (s->mega_ver == 3 && !force_v2)
     Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega3_kernel, dim3(s->mega_grid), dim3(M3_THREADS), params,
                                               s->m3_smem, s->st));
   else
@@ -1142,6 +1148,29 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
             Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, decode_frames_mega3_kernel, M3_THREADS, s->m3_smem));
           }
           if (per_sm3 >= 1) s->mega_ver = 3;
+        }
+        // TMA weight ring, generation 4 (mega4.cuh): the default wherever every skinny-GEMM phase has K % 1024 == 0
+        const bool want4 = !env || env[0] == '4';
+        if (want4) {
+          std::vector<M2Phase> pr = m2_build_program(s.get(), true, true, true, true, nullptr, nullptr, 0, std::min(B, (int)MEGA_TMAX));
+          bool ok4 = true;
+          for (const M2Phase& ph : pr)
+            if (ph.kind == M2_GEMV && !m4_gemv_supported(ph.N, ph.K, ph.flags & PF_DUAL, ph.flags & PF_NORM, ph.xf)) ok4 = false;
+          s->m4_smem = ok4 ? mega4_smem_bytes(d, std::min(B, (int)MEGA_TMAX), max_seq, &s->m4_slots, &s->m4_red2) : 0;
+          {
+            const char* e5 = std::getenv("Q3_M4_SLOTS");
+            if (e5 && s->m4_smem > 0) {
+              const int want_slots = std::max(2, std::min(s->m4_slots, std::atoi(e5)));
+              s->m4_smem -= (size_t)(s->m4_slots - want_slots) * M4_SLOT_BYTES;
+              s->m4_slots = want_slots;
+            }
+          }
+          int per_sm4 = 0;
+          if (s->m4_smem > 0) {
+            Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->m4_smem));
+            Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, decode_frames_mega4_kernel, M4_THREADS, s->m4_smem));
+          }
+          if (per_sm4 >= 1) s->mega_ver = 4;
         }
       } else if (v1_ok) {
         s->mega_ver = 1;

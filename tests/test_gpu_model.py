@@ -237,10 +237,11 @@ def test_full_size_1p7b_batch8_properties():
         assert all((f[0] < 2048) for f in row) and all(max(f[1:]) < 2048 for f in row)
 
 
-@pytest.mark.parametrize("mega", ["1", "2", "3"])
+@pytest.mark.parametrize("mega", ["1", "2", "3", "4"])
 def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
-    """The three generations of the persistent frame kernel -- fence-based grid barriers (Q3_MEGA=1), tagged dataflow
-    phases (2, the default) and the TMA weight-ring variant (3) -- are all held to the same bar on a model whose
+    """The generations of the persistent frame kernel -- fence-based grid barriers (Q3_MEGA=1), tagged dataflow phases (2),
+    the round-1 TMA weight-ring variant (3) and the warp-specialised TMA ring of round 2 (4, the default where every
+    skinny-GEMM K is a multiple of 1024) -- are all held to the same bar on a model whose
     dimensions exercise the register-resident, streaming and ring code paths (hidden 2048 / CP hidden 1024):
     free-running forks from the oracle only at near-ties, identical results on a second run, and across the
     16-frame launch boundary (40 frames = 3 launches, so the session's tag counter is carried between launches)."""
