@@ -13,10 +13,14 @@ checkpoints exist offline); prompts are the synthetic prompt set of SURVEY.md §
 
 `value`  : frames/s with everything resident in HBM (codes and PCM stay on the device), CUDA-event timed.
 `e2e`    : the same step through the host-buffer API (ids in from host memory, codes + PCM copied back to
-           host memory inside the timed region); wall clock bracketed by synchronisation.
+           host memory inside the timed region; at N > 1 also the two collectives of SURVEY.md 8e -- all_gather of the
+           frame counts, gather of the PCM rows to rank 0); wall clock bracketed by synchronisation.
 N > 1    : one process per GPU (torchrun), utterances sharded over ranks, weights replicated, no data-path
-           collective; barrier + max over ranks; `value` = all ranks' frames / that time ("weak" scaling:
-           8 utterances per GPU).
+           collective during decode; barrier + max over ranks; `value` = all ranks' frames / that time ("weak" scaling:
+           8 utterances per GPU).  The line also carries `strong`: BASELINE.json configs[4], a GLOBAL batch of 32
+           utterances split over the N ranks (32/N per GPU), measured the same way.
+`by_batch`: the metric is quoted at batch 1 / 8 / 32: the batch-1 and batch-32 legs run (shorter) in the same process
+           at N = 1 and are reported beside the batch-8 headline, each with its own roofline fraction.
 """
 from __future__ import annotations
 
@@ -42,7 +46,9 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=8, help="utterances per GPU")
     ap.add_argument("--frames", type=int, default=256, help="decode frames per utterance per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=6)
+    ap.add_argument("--cpu-frames", type=int, default=32, help="frames per utterance of a CPU-arm sample")
+    ap.add_argument("--no-by-batch", action="store_true", help="skip the batch-1 / batch-32 legs (N = 1)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (N > 1)")
     return ap.parse_args()
 
 
@@ -86,9 +92,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# one `ncu --set full` capture of decode_frames_mega2_kernel at the bench shape (1.7B, batch 8): 73.30 GB read +
-# 0.42 GB written per 16-frame launch (profiles/r1_mega2_full.summary.txt)
-NCU_TRAFFIC_PER_FRAME = (73.301614e9 + 0.415258e9) / 16.0
+def ncu_traffic(kernel: str, model: str, batch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per FRAME of the decode kernel, from the committed `ncu --set full`
+    capture of this kernel at this shape (profiles/traffic.json, written from the capture's raw page), or None: a
+    number from a profiler run, not a measurement of this run (B200_PROFILING.md)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    for e in json.load(open(p)).get("captures", []):
+        if e["kernel"] == kernel and e["model"] == model and e["batch"] == batch:
+            return {"bytes_per_frame": e["dram_bytes_per_frame"], "source": e["source"]}
+    return None
 
 
 def measured_peaks():
@@ -104,60 +118,204 @@ def build_prompts(spec, n, first):
     return [W.synthetic_prompt(first + i, spec) for i in range(n)]
 
 
-def cpu_reference_run(spec, talker_w, vocoder_w, n_utt, frames, first_prompt=0, threads=None):
-    """The reference's CPU path (F32), restated by the oracle, on the host cores.  Returns (frames, seconds)."""
-    import torch
-    from oracle import generate as OG, model as OM, sampling as osmp, vocoder as OV
-    from qwen3_tts_rs_b200 import spec as S
-    if threads:
+class CpuArm:
+    """The reference's CPU path (F32), restated by the oracle (torch/MKL), on the host cores: one utterance at a time,
+    as the reference runs (it has no batching).  A sample = prefill + `frames` decode frames + vocoder of ONE utterance of
+    the GPU arm's prompt set (utterance index `utt`, seed 42 + utt)."""
+
+    def __init__(self, spec, talker_w, vocoder_w, threads):
+        import torch
+        from oracle import model as OM, vocoder as OV
         torch.set_num_threads(threads)
-    tk, cp = OM.Talker(spec, talker_w, OM.F32P), OM.CodePredictor(spec, talker_w, OM.F32P)
-    voc = OV.Vocoder(spec.vocoder, vocoder_w)
-    cfg = osmp.GenerationConfig(max_new_tokens=frames)
-    prompts = build_prompts(spec, n_utt, first_prompt)
-    total, t0 = 0, time.perf_counter()
-    for i, ids in enumerate(prompts):
-        emb = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
-        fr = OG.prefill_and_generate(tk, cp, emb, ids, cfg, 42 + first_prompt + i)
+        self.spec, self.threads = spec, threads
+        self.tk, self.cp = OM.Talker(spec, talker_w, OM.F32P), OM.CodePredictor(spec, talker_w, OM.F32P)
+        self.voc = OV.Vocoder(spec.vocoder, vocoder_w)
+
+    def sample(self, utt, frames):
+        from oracle import generate as OG, sampling as osmp
+        from qwen3_tts_rs_b200 import spec as S
+        ids = build_prompts(self.spec, 1, utt)[0]
+        t0 = time.perf_counter()
+        emb = self.tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+        fr = OG.prefill_and_generate(self.tk, self.cp, emb, ids, osmp.GenerationConfig(max_new_tokens=frames), 42 + utt)
         if fr:
-            voc.decode(OG.codes_to_tensor(fr))
-        total += len(fr)
-    return total, time.perf_counter() - t0
+            self.voc.decode(OG.codes_to_tensor(fr))
+        return len(fr), time.perf_counter() - t0
+
+
+def workload_config(spec, B, world, F, scaling="weak"):
+    return {"workload": f"{spec.name} CustomVoice(ryan) non-streaming: prefill + {F} decode frames + vocoder, "
+                        f"batch {B} per GPU (BASELINE.json configs[2]), synthetic prompt set of SURVEY.md 8d",
+            "model": spec.name, "batch_per_gpu": B, "global_batch": B * world, "frames_per_step": F,
+            "l2_policy": "inputs larger than L2 (weights 3.9 GB re-streamed every frame; no flush needed)",
+            "vocoder_dtype": "f32"}
 
 
 def run_reference(args, spec, rank, world):
-    """--impl reference: rank 0 alone times the reference's CPU implementation of the path (oracle port,
-    torch F32 on all host cores) on a bounded sample per step."""
+    """--impl reference: rank 0 alone times the reference's CPU implementation of the path (oracle port, torch F32 on all
+    host cores) on the GPU arm's config: every step is a bounded sample of that workload -- one utterance of the same
+    prompt set (step s takes utterance s mod batch, seed 42 + that index), `--cpu-frames` decode frames instead of 256."""
     if rank != 0:
         return
     import torch
     from qwen3_tts_rs_b200 import weights as W
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     tw = W.make_talker_weights(spec, dtype=torch.float32)
     vw = W.make_vocoder_weights(spec.vocoder)
-    frames_per_step = args.cpu_frames
-    for _ in range(args.warmup):
-        cpu_reference_run(spec, tw, vw, 1, 2)
+    arm = CpuArm(spec, tw, vw, cores)
+    F = args.cpu_frames
+    for _ in range(max(1, min(args.warmup, 3))):
+        arm.sample(0, 2)
     tot_f, tot_t = 0, 0.0
     for s in range(args.steps):
-        f, t = cpu_reference_run(spec, tw, vw, 1, frames_per_step, first_prompt=s)
+        f, t = arm.sample(s % args.batch, F)
         tot_f += f
         tot_t += t
     value = tot_f / tot_t
-    sample = f"1 utterance x {frames_per_step} frames per step (prefill + decode loop + vocoder), batch 1, F32"
+    sample = (f"per step: 1 utterance of the batch-{args.batch} prompt set x {F} frames (prefill + decode loop + vocoder), "
+              f"run one at a time as the reference does (no batching), torch F32 (MKL) restatement of the reference CPU path")
     out = {
         "impl": "reference", "metric": "audio_frames_per_sec", "value": value, "unit": "frames/s",
         "rtf": (tot_t / (tot_f * 0.08)) if tot_f else None,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{spec.name} CustomVoice(ryan) non-streaming, reference CPU path (oracle port, torch F32/MKL)",
-                   "model": spec.name, "batch": 1, "frames_per_step": frames_per_step},
+        "config": workload_config(spec, args.batch, max(1, args.gpus), args.frames),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
+
+
+class Leg:
+    """One workload on this rank's GPU: `B` utterances (global utterance indices first..first+B), F frames each."""
+
+    def __init__(self, tts, spec, lib, B, F, first, local_rank):
+        import torch
+        from qwen3_tts_rs_b200 import api, shard
+        self.tts, self.spec, self.B, self.F, self.first = tts, spec, B, F, first
+        self.prompts = build_prompts(spec, B, first)
+        self.seeds = shard.utterance_seeds(42, first, first + B)
+        self.pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in self.prompts]
+        self.lmax = max(len(p[0]) for p in self.pp)
+        self.sess = api.Session(tts.model, B, api.SynthesisOptions(max_length=F), self.seeds, max_seq=self.lmax + F + 8)
+        self.trailing = [list(t[1:]) for t in self.prompts]
+        self.stream = torch.cuda.ExternalStream(lib.q3_session_stream(self.sess.handle), device=torch.device("cuda", local_rank))
+
+    def _prompt(self):
+        s = self.sess
+        s.reset(self.seeds)
+        s.prefill_ids([p[0] for p in self.pp], [p[1] for p in self.pp])
+        s.set_trailing_ids(self.trailing)
+
+    def step_device(self):
+        self._prompt()
+        self.sess.generate_async(self.F)
+        self.sess.vocode(self.F, to_host=False)
+
+    def step_e2e(self):
+        self._prompt()
+        codes, n = self.sess.generate(self.F)
+        pcm = self.sess.vocode(self.F, to_host=True)
+        return codes, n, pcm
+
+    def h2d_bytes(self):
+        return int(sum(len(p[0]) * 8 for p in self.pp) + sum(len(t) * 4 for t in self.trailing))
+
+    def close(self):
+        self.sess.close()
+
+
+def measure(leg, steps, warmup, rank, world, n_total, want_clocks=False, local_rank=0):
+    """Times `steps` steps of one leg: device-resident (CUDA events on the session stream), the decode loop alone, and end
+    to end through the host-buffer API (+ the two collectives at N > 1).  Max over ranks.  Returns a dict on every rank."""
+    import torch
+    import torch.distributed as dist
+    from qwen3_tts_rs_b200 import lib as L, shard
+    lib = L.load()
+    sess, F = leg.sess, leg.F
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        leg.step_device()
+    sess.synchronize()
+    # ---- device-resident.  The working set of one step (3.9 GB of bf16 weights streamed every frame + 0.46 GB vocoder
+    # weights + multi-GB vocoder activations) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
+    clocks = ClockSampler(local_rank) if want_clocks else None
+    barrier()
+    if clocks:
+        clocks.start()
+    launches0 = lib.q3_kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dec_ms = 0.0
+    ev0.record(leg.stream)
+    for _ in range(steps):
+        leg.step_device()
+        dec_ms += sess.timing().decode_ms
+    ev1.record(leg.stream)
+    barrier()
+    ms_dev = ev0.elapsed_time(ev1)
+    launches = lib.q3_kernel_launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    # ---- the decode loop alone (CUDA events around the frame loop of one step)
+    leg._prompt()
+    sess.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(leg.stream)
+    sess.generate_async(F)
+    e1.record(leg.stream)
+    sess.synchronize()
+    loop_ms = e0.elapsed_time(e1)
+    prefill_ms = sess.timing().prefill_ms
+    _, nfr = sess.get_codes(F)
+    frames_run = int(max(nfr)) if len(nfr) else F
+    # ---- end to end: host buffers in and out, and (N > 1) the collectives of the sharded API inside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(steps):
+        codes, n, pcm = leg.step_e2e()
+        d2h = int(codes.nbytes + n.nbytes + pcm.nbytes)
+        if world > 1:
+            all_counts = shard.gather_frame_counts(n.tolist(), n_total, rank, world, device="cuda")
+            rows = shard.gather_pcm(pcm, n.tolist(), all_counts.tolist(), rank, world, leg.spec.vocoder.total_upsample, 0, "cuda")
+            assert (rows is None) == (rank != 0) and (rows is None or len(rows) == n_total)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    frames_step = int(n.sum())
+    times = torch.tensor([ms_dev, e2e_s * 1e3, loop_ms], dtype=torch.float64, device="cuda")
+    fr = torch.tensor([float(frames_step)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
+    ms_dev_max, e2e_ms_max, loop_ms_max = [float(x) for x in times.tolist()]
+    total = float(fr.item())
+    return {"frames_per_step_all_ranks": total, "ms_dev": ms_dev_max, "e2e_ms": e2e_ms_max, "loop_ms": loop_ms_max,
+            "loop_ms_local": loop_ms, "frames_run": frames_run, "prefill_ms": prefill_ms, "vocoder_ms": dec_ms / steps,
+            "launches": int(launches), "clocks": clk, "h2d": leg.h2d_bytes(), "d2h": d2h, "steps": steps,
+            "value": total * steps / (ms_dev_max / 1e3), "e2e_value": total * steps / (e2e_ms_max / 1e3)}
+
+
+def roofline_of(spec, B, lmax, m, kernel, peak, peak_src):
+    """Decode step (one frame for all B rows of this GPU) against the measured HBM copy bandwidth; algorithmic bytes =
+    SURVEY.md 8d bytes_step(B, mean context length)."""
+    from qwen3_tts_rs_b200 import spec as S
+    ctx = lmax + m["frames_run"] / 2.0
+    bytes_step = S.step_bytes(spec, B, ctx)
+    t_frame = (m["loop_ms_local"] / 1e3) / max(1, m["frames_run"])
+    achieved = bytes_step / t_frame / 1e9
+    tr = ncu_traffic(kernel, spec.name, B)
+    return {"kernel": f"{kernel}, per frame (one persistent cooperative launch runs 16 frames: 15 code-predictor passes + "
+                      f"{spec.layers}-layer talker step + codec head + sampler for all rows)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "traffic": tr["bytes_per_frame"] if tr else None,
+            "traffic_source": tr["source"] if tr else "no ncu --set full capture of this kernel at this shape is committed",
+            "algorithmic_bytes_per_launch": bytes_step, "launch_ms": t_frame * 1e3}
 
 
 def main():
@@ -172,7 +330,6 @@ def main():
         run_reference(args, spec, rank, world)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
     from qwen3_tts_rs_b200 import api, lib as L, weights as W
@@ -186,153 +343,92 @@ def main():
     vw = W.make_vocoder_weights(spec.vocoder)
     tts = api.Qwen3TTS.from_weights(spec, tw, vw, device=local_rank)
     lib = L.load()
-
-    from qwen3_tts_rs_b200 import shard
+    kernel = {4: "decode_frames_mega4_kernel", 3: "decode_frames_mega3_kernel", 1: "decode_frames_mega_kernel"}.get(
+        int(os.environ.get("Q3_MEGA", "4") or 4), "decode_frames_mega2_kernel")
+    peak, peak_src = measured_peaks()
     B, F = args.batch, args.frames
-    first, last = shard.shard_range(B * world, rank, world)       # weak scaling: B utterances per GPU
-    prompts = build_prompts(spec, B, first)
-    seeds = shard.utterance_seeds(42, first, last)
-    opts = api.SynthesisOptions(max_length=F)
-    pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
-    lmax = max(len(p[0]) for p in pp)
-    sess = api.Session(tts.model, B, opts, seeds, max_seq=lmax + F + 8)
-    trailing = [list(t[1:]) for t in prompts]
-    stream = torch.cuda.ExternalStream(lib.q3_session_stream(sess.handle), device=torch.device("cuda", local_rank))
-    up = spec.vocoder.total_upsample
+    warm = max(args.warmup, 3)
 
-    def step_device():
-        sess.reset(seeds)
-        sess.prefill_ids([p[0] for p in pp], [p[1] for p in pp])
-        sess.set_trailing_ids(trailing)
-        sess.generate_async(F)
-        sess.vocode(F, to_host=False)
+    # ---- headline: weak scaling, B utterances per GPU ------------------------------------------------
+    leg = Leg(tts, spec, lib, B, F, rank * B, local_rank)
+    m = measure(leg, args.steps, warm, rank, world, B * world, want_clocks=True, local_rank=local_rank)
+    lmax = leg.lmax
+    leg.close()
 
-    def step_e2e():
-        sess.reset(seeds)
-        sess.prefill_ids([p[0] for p in pp], [p[1] for p in pp])
-        sess.set_trailing_ids(trailing)
-        codes, n = sess.generate(F)
-        pcm = sess.vocode(F, to_host=True)
-        return codes, n, pcm
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- warm-up ---------------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    sess.synchronize()
-
-    # ---- timed: device-resident ---------------------------------------------------------------------
-    # The working set of one step (3.9 GB of bf16 weights streamed ~16x per frame + 0.46 GB vocoder weights
-    # + multi-GB vocoder activations) is far larger than the 126 MB L2, so no explicit L2 flush is needed.
-    clocks = ClockSampler(local_rank)
-    barrier()
-    clocks.start()
-    launches0 = lib.q3_kernel_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    gen_ms = dec_ms = 0.0
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-        t = sess.timing()
-        gen_ms += t.generation_ms if t.generation_ms else 0.0
-        dec_ms += t.decode_ms
-    ev1.record(stream)
-    barrier()
-    ms_dev = ev0.elapsed_time(ev1)
-    launches = lib.q3_kernel_launch_count() - launches0
-    clk = clocks.stop()
-
-    # decode-loop-only timing (CUDA events around the frame loop of one step)
-    sess.reset(seeds)
-    sess.prefill_ids([p[0] for p in pp], [p[1] for p in pp])
-    sess.set_trailing_ids(trailing)
-    sess.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    sess.generate_async(F)
-    e1.record(stream)
-    sess.synchronize()
-    loop_ms = e0.elapsed_time(e1)
-    prefill_ms = sess.timing().prefill_ms
-    _, nfr = sess.get_codes(F)
-    frames_run = int(max(nfr)) if len(nfr) else F
-
-    # ---- timed: end to end through the host-buffer API ----------------------------------------------------
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        codes, n, pcm = step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    frames_step = int(n.sum())
-    # the only collective of the path: per-utterance frame counts gathered to every rank
-    all_counts = shard.gather_frame_counts(n.tolist(), B * world, rank, world, device="cuda")
-    assert int(all_counts.sum()) >= frames_step
-
-    times = torch.tensor([ms_dev, e2e_s * 1e3, loop_ms], dtype=torch.float64, device="cuda")
-    fr = torch.tensor([float(frames_step)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
-    ms_dev_max, e2e_ms_max, loop_ms_max = [float(x) for x in times.tolist()]
-    total_frames_step = float(fr.item())
+    # ---- batch 1 / 32 legs (N = 1) and the strong-scaling leg (N > 1: global batch 32 split over the ranks) -------
+    by_batch, strong = None, None
+    if world == 1 and not args.no_by_batch:
+        by_batch = {}
+        for b in (1, 32):
+            if b == B:
+                continue
+            lg = Leg(tts, spec, lib, b, F, 0, local_rank)
+            mb = measure(lg, 2, 3, rank, world, b)
+            by_batch[str(b)] = (mb, lg.lmax)
+            lg.close()
+    if world > 1 and not args.no_strong and 32 % world == 0:
+        bs = 32 // world
+        lg = Leg(tts, spec, lib, bs, F, rank * bs, local_rank)
+        strong = (measure(lg, max(2, min(args.steps, 5)), 3, rank, world, 32), lg.lmax, bs)
+        lg.close()
 
     if rank == 0:
-        value = total_frames_step * args.steps / (ms_dev_max / 1e3)
-        e2e_value = total_frames_step * args.steps / (e2e_ms_max / 1e3)
-        peak, peak_src = measured_peaks()
-        # roofline of the decode step (one replay of the frame graph = one frame for all B rows):
-        # algorithmic bytes = SURVEY.md §8d bytes_step(B, mean context length)
-        ctx = lmax + frames_run / 2.0
-        bytes_step = S.step_bytes(spec, B, ctx)
-        t_frame = (loop_ms / 1e3) / max(1, frames_run)
-        achieved = bytes_step / t_frame / 1e9
+        def summary(mm, b, lm):
+            total = mm["frames_per_step_all_ranks"]
+            return {"batch_per_gpu": b, "value": mm["value"], "unit": "frames/s",
+                    "rtf": (mm["ms_dev"] / 1e3) / (total * mm["steps"] * 0.08),
+                    "e2e": mm["e2e_value"], "e2e_rtf": (mm["e2e_ms"] / 1e3) / (total * mm["steps"] * 0.08),
+                    "ms_per_frame": mm["loop_ms"] / max(1, mm["frames_run"]), "vocoder_ms": mm["vocoder_ms"],
+                    "steps": mm["steps"], "roofline_frac": roofline_of(spec, b, lm, mm, kernel, peak, peak_src)["frac"]}
+
+        total = m["frames_per_step_all_ranks"]
         out = {
-            "metric": "audio_frames_per_sec", "value": value, "unit": "frames/s",
-            "rtf": (ms_dev_max / 1e3) / (total_frames_step * args.steps * 0.08),
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev_max / args.steps,
+            "metric": "audio_frames_per_sec", "value": m["value"], "unit": "frames/s",
+            "rtf": (m["ms_dev"] / 1e3) / (total * args.steps * 0.08),
+            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": m["ms_dev"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{spec.name} CustomVoice(ryan) non-streaming: prefill + {F} decode frames + vocoder, "
-                                   f"batch {B} per GPU (BASELINE.json configs[2])",
-                       "model": spec.name, "batch_per_gpu": B, "global_batch": B * world, "frames_per_step": F,
-                       "l2_policy": "inputs larger than L2 (weights 3.9 GB re-streamed every frame; no flush needed)",
-                       "vocoder_dtype": "f32"},
-            "breakdown_ms_per_step": {"decode_loop": loop_ms_max, "frames_in_loop": frames_run,
-                                      "ms_per_frame": loop_ms_max / max(1, frames_run),
-                                      "vocoder": dec_ms / args.steps, "prefill": prefill_ms,
-                                      "vocoder_tflops_f32_equiv": (total_frames_step / world) * 4.959e9 / (dec_ms / args.steps / 1e3) / 1e12},
-            "roofline": {"kernel": "decode_frames_mega2_kernel, per frame (one persistent cooperative launch runs 16 frames: 15 code-predictor "
-                                   "passes + 28-layer talker step + codec head + sampler for all rows)",
-                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "peak_source": peak_src,
-                         # dram__bytes_read + dram__bytes_write of one 16-frame launch / 16 (profiles/r1_mega2_full.summary.txt);
-                         # below the algorithmic bytes because part of the code-predictor weights stay in L2 between passes
-                         "traffic": NCU_TRAFFIC_PER_FRAME if (spec.name == "1.7b" and B == 8) else None,
-                         "algorithmic_bytes_per_launch": bytes_step, "launch_ms": t_frame * 1e3},
-            "e2e": {"value": e2e_value, "unit": "frames/s",
-                    "rtf": (e2e_ms_max / 1e3) / (total_frames_step * args.steps * 0.08),
-                    "h2d_bytes_per_step": int(sum(len(p[0]) * 8 for p in pp) + sum(len(t) * 4 for t in trailing)),
-                    "d2h_bytes_per_step": int(codes.nbytes + n.nbytes + pcm.nbytes)},
-            "gpu_launches": int(launches),
-            "clocks": clk,
+            "config": workload_config(spec, B, world, F),
+            "breakdown_ms_per_step": {"decode_loop": m["loop_ms"], "frames_in_loop": m["frames_run"],
+                                      "ms_per_frame": m["loop_ms"] / max(1, m["frames_run"]),
+                                      "vocoder": m["vocoder_ms"], "prefill": m["prefill_ms"],
+                                      "vocoder_tflops_f32_equiv": (total / world) * 4.959e9 / (m["vocoder_ms"] / 1e3) / 1e12},
+            "roofline": roofline_of(spec, B, lmax, m, kernel, peak, peak_src),
+            "e2e": {"value": m["e2e_value"], "unit": "frames/s",
+                    "rtf": (m["e2e_ms"] / 1e3) / (total * args.steps * 0.08),
+                    "h2d_bytes_per_step": m["h2d"], "d2h_bytes_per_step": m["d2h"],
+                    "collectives_in_timed_region": (["all_gather(frame counts)", "gather(pcm -> rank 0)"] if world > 1 else [])},
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
         }
+        if by_batch is not None:
+            out["by_batch"] = {str(B): summary(m, B, lmax)}
+            for k, (mb, lm) in by_batch.items():
+                out["by_batch"][k] = summary(mb, int(k), lm)
+        if strong is not None:
+            ms_, lm, bs = strong
+            out["strong"] = dict(summary(ms_, bs, lm), scaling="strong", global_batch=32,
+                                 workload="BASELINE.json configs[4]: 32 utterances sharded data-parallel over the ranks")
         if not args.no_cpu_baseline:
-            import torch as _t
+            # the reference's CPU path on this box's host cores: median of 3 bounded samples (utterances 0, 1, 2 of the same
+            # prompt set, --cpu-frames frames each), after a warm-up sample
             cores = os.cpu_count() or 1
-            tw32 = {k: v.float() for k, v in tw.items()}
-            cpu_reference_run(spec, tw32, vw, 1, 1, threads=cores)          # warm-up
-            f, t = cpu_reference_run(spec, tw32, vw, 1, args.cpu_frames, threads=cores)
-            out["cpu_baseline"] = {"value": f / t, "unit": "frames/s", "cores": cores, "kind": "port",
-                                   "rtf": t / (f * 0.08) if f else None,
-                                   "sample": f"1 utterance x {args.cpu_frames} frames (prefill + decode loop + vocoder), batch 1, "
-                                             "torch F32 (MKL) restatement of the reference CPU path"}
+            arm = CpuArm(spec, {k: v.float() for k, v in tw.items()}, vw, cores)
+            arm.sample(0, 2)
+            rates = []
+            for u in range(3):
+                f, t = arm.sample(u % B, max(2, args.cpu_frames // 2))
+                rates.append(f / t)
+            rates.sort()
+            med = rates[1]
+            out["cpu_baseline"] = {"value": med, "unit": "frames/s", "cores": cores, "kind": "port",
+                                   "rtf": 1.0 / (med * 0.08), "samples": rates,
+                                   "sample": f"median of 3 samples, each 1 utterance x {max(2, args.cpu_frames // 2)} frames (prefill + decode loop "
+                                             "+ vocoder), batch 1, torch F32 (MKL) restatement of the reference CPU path"}
+            b1 = out.get("by_batch", {}).get("1")
+            if b1:
+                # per-stream comparison: one utterance at a time on both sides
+                out["cpu_baseline"]["gpu_batch1_e2e_over_cpu"] = b1["e2e"] / med
         print(json.dumps(out), flush=True)
-    sess.close()
     if world > 1:
         dist.destroy_process_group()
 

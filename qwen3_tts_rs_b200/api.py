@@ -239,6 +239,13 @@ class Session:
         L.check(self.lib.q3_generate(self.handle, max_frames, _ptr(codes), _ptr(n)))
         return codes, n
 
+    def decode_generation(self) -> int:
+        """0 = multi-kernel CUDA graph, 1..4 = generation of the persistent frame kernel this session runs on (debug aid)."""
+        fn = self.lib.q3_debug_decode_generation
+        fn.argtypes = [C.c_void_p]
+        fn.restype = C.c_int
+        return int(fn(self.handle))
+
     def generate_tapped(self, max_frames: int):
         """q3_debug_generate_tapped (test aid): q3_generate with the loop's decision inputs read back every frame.
         Returns (codes, n_frames, taps) with taps = dict(first_logits [B,V], logits [F,B,V], cp_logits [F,15,B,cpV],

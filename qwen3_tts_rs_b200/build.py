@@ -28,24 +28,37 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+# Two libraries from the same sources:
+#   libq3tts_b200.so      the product: the dataflow kernel (mega2.cuh) and the TMA-ring kernel (mega4.cuh) only, profiling
+#                         hooks compiled out (code that never runs still costs instruction fetch in a run-once-per-phase kernel)
+#   libq3tts_b200_dev.so  + the historical generations (Q3_MEGA=1 / 3) and the profiling hooks (tools/profile_*.py, and the
+#                         tests that keep the old generations against the oracle); selected with Q3TTS_LIB=dev
+VARIANTS = {"": [], "_dev": ["-DQ3_ALL_GENERATIONS=1", "-DQ3_PROF=1"]}
+
+
+def lib_path(variant: str = "") -> str:
+    return os.path.join(HERE, f"libq3tts_b200{variant}.so")
+
+
+def build(force: bool = False, verbose: bool = False, variants=None) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(HERE, "..", "include", "q3tts.h"))
-    objs = []
-    jobs = []
-    for src in SOURCES:
-        sp = os.path.join(CSRC, src)
-        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        objs.append(obj)
-        if force or _stale(obj, [sp] + headers):
-            jobs.append((sp, obj))
+    variants = list(VARIANTS) if variants is None else variants
+    jobs, objs = [], {v: [] for v in variants}
+    for v in variants:
+        for src in SOURCES:
+            sp = os.path.join(CSRC, src)
+            obj = os.path.join(CSRC, src.replace(".cu", f"{v}.o"))
+            objs[v].append(obj)
+            if force or _stale(obj, [sp] + headers):
+                jobs.append((sp, obj, VARIANTS[v]))
 
     def compile_one(job):
-        sp, obj = job
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", sp, "-o", obj]
+        sp, obj, defs = job
+        cmd = [_nvcc()] + NVCC_FLAGS + defs + ["-c", sp, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = os.path.join(CSRC, os.path.basename(obj) + ".ptxas.log")
-        with open(log, "w") as f:      # register / spill report, kept in the tree; compile times dropped so it is stable
+        with open(log, "w") as f:      # register / spill report (git-ignored build artefact)
             f.write("".join(ln for ln in r.stderr.splitlines(True) if "Compile time" not in ln))
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {sp}:\n{r.stderr[-6000:]}")
@@ -56,11 +69,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if jobs:
         with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
             list(ex.map(compile_one, jobs))
-    if force or jobs or _stale(LIB, objs):
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
+    for v in variants:
+        lib = lib_path(v)
+        if force or jobs or _stale(lib, objs[v]):
+            cmd = [_nvcc(), "-shared", "-o", lib] + objs[v] + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")
     return LIB
 
 

@@ -216,6 +216,13 @@ __device__ __forceinline__ void mega_prefetch_rows(const bf16* W, const bf16* W2
   if (W2 != nullptr) l2_prefetch_bulk(W2 + (size_t)r0 * K, (size_t)(r1 - r0) * K * 2);
 }
 
+constexpr int ATT_U = 8;   // cache rows per warp whose loads are in flight together (mega_attn, m2_attn)
+constexpr int MEGA_MAX_LAYERS = 40;
+
+// The first-generation kernel below (fence-based grid barriers) is history: it is compiled only into the development
+// library (-DQ3_ALL_GENERATIONS, libq3tts_b200_dev.so) where the tests keep it against the oracle; the product library
+// carries a stub so that the shared host code links, and q3_session_create refuses Q3_MEGA=1 there.
+#ifdef Q3_ALL_GENERATIONS
 // Cross-warp combine (fixed order), fused epilogue, partial sums of squares, barrier arrive: the common tail of
 // the skinny-GEMM phases.  `red` holds the warps' partial sums as [nt][m][token col 0..7][warp][CTA-local row] f32
 // (column stride 16*R + 4 floats, R = 16 * n_tiles): the combine reads 32 consecutive rows per warp and the
@@ -753,7 +760,6 @@ struct AttnP {
   int pos_add, S, B, heads, kv_heads, max_seq;
 };
 
-constexpr int ATT_U = 8;   // cache rows per warp whose loads are in flight together
 __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsigned char* smem) {
   float* sc0 = reinterpret_cast<float*>(smem);          // [max_seq]
   float* sc1 = sc0 + p.max_seq;
@@ -911,7 +917,6 @@ __device__ __noinline__ void mega_attn(const MegaArgs& a, const AttnP& p, unsign
 // Phase descriptors live in SHARED memory: thread 0 fills them, everybody reads them (broadcast).  Building
 // them per thread on the stack would cost ~150 B of local-memory traffic per thread per phase (6 GB of DRAM
 // writes per frame at 75 k threads x 546 phases -- measured with ncu before this change).
-constexpr int MEGA_MAX_LAYERS = 40;
 struct MegaShared {
   LayerW layers[MEGA_MAX_LAYERS];   // talker layers then code-predictor layers (pointer tables read by every descriptor fill)
   MegaArgs a;
@@ -1127,6 +1132,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(con
     }
   }
 }
+
+#else
+__global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega_kernel(const MegaArgs) {}
+#endif
 
 // Shared memory of the persistent kernel for a given model / batch / grid; returns 0 when a phase does not fit
 // the kernel's static limits (then the multi-kernel path is used).

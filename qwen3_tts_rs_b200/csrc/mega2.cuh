@@ -31,6 +31,16 @@
 
 typedef unsigned long long u64;
 
+// Profiling hooks (phase stamps of block 0, per-CTA arrival stamps, tag re-read counters) are compiled in only with
+// -DQ3_PROF=1 (the tools' library, libq3tts_b200_prof.so).  Every phase function of the persistent kernels runs ONCE per
+// phase and the ~10 functions of a frame evict each other from the instruction caches (ncu: 111 instruction-cache misses
+// per phase per SM = the whole function body), so code that is never executed in production still costs fetch bandwidth.
+#ifdef Q3_PROF
+#define M2_PROF_ENABLED true
+#else
+#define M2_PROF_ENABLED false
+#endif
+
 enum M2Kind { M2_GEMV = 0, M2_ATTN = 1, M2_PROLOGUE = 2, M2_GATHER = 3, M2_FINISH = 4, M2_COPYIN = 5, M2_SAMPLE = 6 };
 enum M2Fmt { XF_BF16T = 0, XF_F32T = 1, XF_GATHER = 2, XF_NONE = 3 };
 enum M2Flags { PF_WAIT_ACQ = 1, PF_ARRIVE_REL = 2, PF_DUAL = 4, PF_NORM = 8, PF_CP = 16, PF_CP0 = 32 };
@@ -170,7 +180,7 @@ __device__ __forceinline__ void m2_wait(M2Sync& gs, int flags) {
 // callers make sure every thread's stores of the phase were issued (a __syncthreads) before this
 __device__ __forceinline__ void m2_arrive(M2Sync& gs, int flags) {
   if (threadIdx.x == 0) {
-    if (gs.arr != nullptr) {
+    if (M2_PROF_ENABLED && gs.arr != nullptr) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       gs.arr[3 * gs.G + blockIdx.x] = t;
@@ -182,7 +192,7 @@ __device__ __forceinline__ void m2_arrive(M2Sync& gs, int flags) {
 
 // profiling (prof_mode 2): stamp k (0 wait passed, 1 activations ready, 2 MMA loop done, 3 arrive) of this CTA
 __device__ __forceinline__ void m2_stamp(M2Sync& gs, int k) {
-  if (gs.arr != nullptr && threadIdx.x == 0) {
+  if (M2_PROF_ENABLED && gs.arr != nullptr && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     gs.arr[k * gs.G + blockIdx.x] = t;
@@ -191,7 +201,7 @@ __device__ __forceinline__ void m2_stamp(M2Sync& gs, int k) {
 __device__ unsigned int g_prof2_idx;
 __shared__ unsigned int s_prof2_idx;
 __device__ __forceinline__ void prof2(const M2Args& a, int tag) {
-  if (a.prof != nullptr && a.prof_mode != 2 && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (M2_PROF_ENABLED && a.prof != nullptr && a.prof_mode != 2 && blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     const unsigned i = s_prof2_idx++;
@@ -316,7 +326,7 @@ __device__ __forceinline__ void m2_tail(const M2Args& a, const M2Phase& p, const
                                         const uint32_t tag) {
   constexpr int NM = DUAL ? 2 : 1;
   const int tid = threadIdx.x, lane = tid & 31, T = p.T;
-  const bool prof_on = a.prof != nullptr;
+  const bool prof_on = M2_PROF_ENABLED && a.prof != nullptr;
   const int red_r = n_tiles << 4, red_cs = 16 * red_r + 4;
   if (prof_on) m2_stamp(gs, 2);
   m2_csync();
@@ -430,7 +440,7 @@ __device__ __noinline__ unsigned long long m2_gemv(const M2Args& a, const M2Phas
   float* part_s = reinterpret_cast<float*>(smem) + 16;
   float* red = reinterpret_cast<float*>(smem + M2_RED_OFF);
   const int K = p.K, T = p.T;
-  const bool prof_on = a.prof != nullptr;      // one shared-memory read instead of one per stamp
+  const bool prof_on = M2_PROF_ENABLED && a.prof != nullptr;      // one shared-memory read instead of one per stamp
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const uint32_t xtag = tag - 1u;
   int r0, r1;
@@ -528,7 +538,7 @@ __device__ __noinline__ unsigned long long m2_gemv(const M2Args& a, const M2Phas
         }
       }
       if (XF == XF_GATHER || !__any_sync(0xffffffffu, bad != 0)) break;
-      if (gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+      if (M2_PROF_ENABLED && gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
       if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 3000000 + (int)gs.epoch); break; }
     }
   };
@@ -563,7 +573,7 @@ __device__ __noinline__ unsigned long long m2_gemv(const M2Args& a, const M2Phas
           if (XC > 1) sq[nt] += sqa[XC - 1][nt];
         }
         if (!__any_sync(0xffffffffu, bad != 0)) break;
-        if (gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+        if (M2_PROF_ENABLED && gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
         if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 3500000 + (int)gs.epoch); break; }
       }
     } else {
@@ -646,7 +656,7 @@ __device__ __noinline__ unsigned long long m2_gemv(const M2Args& a, const M2Phas
 #pragma unroll
               for (int i = 0; i < 4; ++i) bad |= slot_tag(xr[nt][u][i]) ^ xtag;
           if (!__any_sync(0xffffffffu, bad != 0)) break;
-          if (gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+          if (M2_PROF_ENABLED && gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
       if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 4000000 + (int)gs.epoch); break; }
           load_x_raw(c);
         }
@@ -716,7 +726,7 @@ __device__ __noinline__ unsigned long long m2_gemv_small(const M2Args& a, const 
   float* part_s = reinterpret_cast<float*>(smem) + 16;
   float* red = reinterpret_cast<float*>(smem + M2_RED_OFF);
   const int K = p.K;
-  const bool prof_on = a.prof != nullptr;
+  const bool prof_on = M2_PROF_ENABLED && a.prof != nullptr;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
   const uint32_t xtag = tag - 1u;
   constexpr int NM = DUAL ? 2 : 1;
@@ -790,7 +800,7 @@ __device__ __noinline__ unsigned long long m2_gemv_small(const M2Args& a, const 
             if (xrow[nt] != nullptr) xv[c][u][nt] = m2_load_x8<XF>(xrow[nt], koff0 + (c * JU + u) * 512, xtag, bad, sq[nt]);
           }
       if (XF == XF_GATHER || !__any_sync(0xffffffffu, bad != 0)) break;
-      if (gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+      if (M2_PROF_ENABLED && gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
       if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 5000000 + (int)gs.epoch); break; }
     }
   }
@@ -910,7 +920,7 @@ constexpr int M2_ATT_FAST_L = 16;
 __device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
                                                    const uint32_t tag) {
   const bool cp = (p.flags & PF_CP) != 0;
-  const bool prof_on = a.prof != nullptr;
+  const bool prof_on = M2_PROF_ENABLED && a.prof != nullptr;
   const int max_seq = cp ? a.cp_max_seq : a.max_seq;
   const bf16* cos_tab = cp ? a.cp_cos : a.t_cos;
   const bf16* sin_tab = cp ? a.cp_sin : a.t_sin;
@@ -976,7 +986,7 @@ __device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phas
           s1 = ld_slot(src + 32 + lane);
           const uint32_t bad = (slot_tag(s0) ^ xtag) | (slot_tag(s1) ^ xtag);
           if (!__any_sync(0xffffffffu, bad != 0)) break;
-          if (gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+          if (M2_PROF_ENABLED && gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
       if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 6000000 + (int)gs.epoch); break; }
         }
         float v[4] = {bf_lo(slot_val(s0)), bf_hi(slot_val(s0)), bf_lo(slot_val(s1)), bf_hi(slot_val(s1))};
@@ -1206,7 +1216,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_frames_mega2_kernel(co
     return;
   }
   const uint32_t tag0 = __ldcg(a.tag_ctr);
-  const bool prof_any = a.prof != nullptr;
+  const bool prof_any = M2_PROF_ENABLED && a.prof != nullptr;
   uint32_t seq = 0;
   bool stop = false;
   m2_arrive(gs, PF_ARRIVE_REL);       // every phase waits for its predecessor's arrive; this is the first phase's

@@ -54,6 +54,18 @@ __device__ __forceinline__ void m3_bulk_g2s(uint32_t dst, const void* src, uint3
                : "memory");
 }
 
+// The round-1 ring kernel is history (slower than the dataflow kernel, superseded by mega4.cuh): compiled only into the
+// development library (-DQ3_ALL_GENERATIONS); the product library carries a stub and refuses Q3_MEGA=3.
+// which (K, dual, norm, input format) combinations the ring kernel implements
+__host__ __device__ inline bool m3_gemv_supported(int K, bool dual, bool norm, int xf, int T) {
+  if (dual) return norm && xf == XF_F32T && (K == 1024 || K == 2048);
+  if (norm) return xf == XF_BF16T && (K == 1024 || K == 2048);
+  if (xf == XF_GATHER) return K == 2048;
+  if (xf != XF_BF16T) return false;
+  return K == 1024 || K == 2048 || K == 3072 || (K == 6144 && T <= 8);
+}
+
+#ifdef Q3_ALL_GENERATIONS
 // CTA-wide bookkeeping in shared memory
 struct M3Shared {
   M2Args a;
@@ -208,15 +220,6 @@ __device__ __noinline__ M3State m3_gemv(M3Shared& sh, const M2Phase& p, unsigned
   m2_tail<DUAL, NT>(a, p, nullptr, red, rres, r0, r1, n_tiles, gs, tag);
   st.epoch = gs.epoch; st.dead = gs.dead; st.cq = cq;
   return st;
-}
-
-// which (K, dual, norm, input format) combinations the ring kernel implements
-__host__ __device__ inline bool m3_gemv_supported(int K, bool dual, bool norm, int xf, int T) {
-  if (dual) return norm && xf == XF_F32T && (K == 1024 || K == 2048);
-  if (norm) return xf == XF_BF16T && (K == 1024 || K == 2048);
-  if (xf == XF_GATHER) return K == 2048;
-  if (xf != XF_BF16T) return false;
-  return K == 1024 || K == 2048 || K == 3072 || (K == 6144 && T <= 8);
 }
 
 __device__ __forceinline__ M3State m3_gemv_dispatch(M3Shared& sh, const M2Phase& p, unsigned char* ring, unsigned char* work,
@@ -454,6 +457,10 @@ __global__ void __launch_bounds__(M3_THREADS, 1) decode_frames_mega3_kernel(cons
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.tag_ctr = tag0 + q + (stop ? 1u : 0u);
 }
+
+#else
+__global__ void __launch_bounds__(M3_THREADS, 1) decode_frames_mega3_kernel(const M2Args) {}
+#endif
 
 static size_t mega3_smem_bytes(const q3_model_desc& d, int B, int max_seq, int grid) {
   const size_t work = mega2_smem_bytes(d, B, max_seq, grid, 0);   // work area only (no program in shared memory)

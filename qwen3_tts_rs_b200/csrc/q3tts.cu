@@ -1090,6 +1090,10 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
     // persistent frame kernel: batch <= 8 (16 tokens in the CP prefill pass), needs one resident CTA per SM
     const char* env = std::getenv("Q3_MEGA");
     const bool want = !(env && env[0] == '0');
+#ifndef Q3_ALL_GENERATIONS
+    Q3_REQUIRE(!(env && (env[0] == '1' || env[0] == '3')), Q3_ERR_UNSUPPORTED,
+               "Q3_MEGA=1 / 3 (the historical generations of the persistent kernel) are only built into libq3tts_b200_dev.so");
+#endif
     s->mega_smem = mega_smem_bytes(d, B, max_seq, m->num_sms);
     s->bar.alloc(64);
     s->bar.zero();
@@ -1107,6 +1111,10 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
     }
     s->mega_ver = (env && env[0] == '1') ? 1 : 2;
     const bool v1_ok = s->use_mega;
+    (void)v1_ok;
+#ifndef Q3_ALL_GENERATIONS
+    s->use_mega = false;             // the first generation is a stub here: only the dataflow / ring kernels below may enable it
+#endif
     const bool dims_ok = d.layers + d.cp_layers <= MEGA_MAX_LAYERS && d.hidden % 32 == 0 && d.cp_hidden % 32 == 0 && d.inter % 32 == 0 &&
                          d.cp_inter % 32 == 0 && d.codec_vocab % 16 == 0 && d.cp_vocab % 16 == 0;
     // the dataflow generation also takes batches 9..16 (code-predictor pass 0 in two row groups)
@@ -1149,8 +1157,10 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
           }
           if (per_sm3 >= 1) s->mega_ver = 3;
         }
-        // TMA weight ring, generation 4 (mega4.cuh): the default wherever every skinny-GEMM phase has K % 1024 == 0
-        const bool want4 = !env || env[0] == '4';
+        // TMA weight ring, generation 4 (mega4.cuh): opt-in (Q3_MEGA=4).  Measured on B200 (1.7B, batch 8) it is 1.47x
+        // SLOWER than the dataflow kernel (4.30 vs 2.93 ms per frame, profiles/r2_mega4_vs_mega2.md), so the dataflow
+        // kernel stays the default; models with a skinny-GEMM K that is not a multiple of 1024 cannot use it at all.
+        const bool want4 = env && env[0] == '4';
         if (want4) {
           std::vector<M2Phase> pr = m2_build_program(s.get(), true, true, true, true, nullptr, nullptr, 0, std::min(B, (int)MEGA_TMAX));
           bool ok4 = true;
@@ -1172,8 +1182,10 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
           }
           if (per_sm4 >= 1) s->mega_ver = 4;
         }
+#ifdef Q3_ALL_GENERATIONS
       } else if (v1_ok) {
         s->mega_ver = 1;
+#endif
       } else {
         s->use_mega = false;
       }
@@ -1719,6 +1731,42 @@ q3_status q3_debug_generate_tapped(q3_session* s, int32_t max_frames, uint32_t* 
   Q3_CHECK_CUDA(cudaEventRecord(s->ev0, s->st));
   Q3_CHECK_CUDA(cudaEventRecord(s->ev1, s->st));
   return q3_get_codes(s, max_frames, codes, n_frames);
+  Q3_API_END
+}
+
+// Debug aid: which decode engine the session runs on: 0 = multi-kernel CUDA graph, 1 / 2 / 3 / 4 = generation of the persistent
+// frame kernel (mega.cuh, mega2.cuh, mega3.cuh, mega4.cuh).  Tests use it to make sure a requested generation was not silently
+// replaced by a fallback.
+int q3_debug_decode_generation(q3_session* s) { return (s && s->use_mega) ? s->mega_ver : 0; }
+
+// Debug aid (race hunting): the first `n_ph` phases of the code-predictor program of one frame, then the raw tagged
+// activation buffers (8-byte slots {payload, tag}) copied back.  sizes in bytes: x 16*H*4, qkv 16*nh*4, attn 16*qd*4,
+// h1 16*H*8, act 16*I*4 with H/I the larger of the talker / code-predictor dimensions (see q3_session_create).
+q3_status q3_debug_cp_prefix(q3_session* s, const uint16_t* last_hidden, const uint32_t* sem_tokens, int32_t n_ph, void* x_out,
+                             void* qkv_out, void* attn_out, void* h1_out, void* act_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && last_hidden && sem_tokens && s->use_mega && s->mega_ver >= 2 && s->B <= MEGA_TMAX, Q3_ERR_STATE, "needs the persistent path");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->last_hidden.p, last_hidden, (size_t)s->B * d.hidden * 2, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->cur_tok.p, sem_tokens, s->B * 4, cudaMemcpyHostToDevice, s->st));
+  ensure_scratch(s, 2 * s->B);
+  std::vector<M2Phase> pr = m2_build_program(s, true, false, false, false, nullptr, nullptr);
+  if (n_ph > 0 && n_ph < (int)pr.size()) pr.resize(n_ph);
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  s->m2_prog_tmp.ensure(pr.size() * sizeof(M2Phase));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_prog_tmp.p, pr.data(), pr.size() * sizeof(M2Phase), cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  M2Args a = mega2_args(s);
+  a.n_frames = 1; a.do_sample = 0;
+  mega2_launch(s, a, s->m2_prog_tmp, (int)pr.size());
+  if (x_out) Q3_CHECK_CUDA(cudaMemcpyAsync(x_out, s->m2_x.p, s->m2_x.bytes, cudaMemcpyDeviceToHost, s->st));
+  if (qkv_out) Q3_CHECK_CUDA(cudaMemcpyAsync(qkv_out, s->m2_qkv.p, s->m2_qkv.bytes, cudaMemcpyDeviceToHost, s->st));
+  if (attn_out) Q3_CHECK_CUDA(cudaMemcpyAsync(attn_out, s->m2_attn.p, s->m2_attn.bytes, cudaMemcpyDeviceToHost, s->st));
+  if (h1_out) Q3_CHECK_CUDA(cudaMemcpyAsync(h1_out, s->m2_h1.p, s->m2_h1.bytes, cudaMemcpyDeviceToHost, s->st));
+  if (act_out) Q3_CHECK_CUDA(cudaMemcpyAsync(act_out, s->m2_act.p, s->m2_act.bytes, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  mega2_check_watchdog(s);
   Q3_API_END
 }
 

@@ -13,7 +13,10 @@ from typing import Optional
 from .spec import ModelSpec
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libq3tts_b200.so")
+# Q3TTS_LIB=dev selects the development library (historical kernel generations + profiling hooks, build.py); read once, at
+# the first load of the process
+LIB_PATH = os.path.join(HERE, "libq3tts_b200_dev.so" if os.environ.get("Q3TTS_LIB") == "dev" else "libq3tts_b200.so")
+IS_DEV = os.environ.get("Q3TTS_LIB") == "dev"
 
 Q3_BF16, Q3_F32 = 0, 1
 STATUS = {0: "Q3_OK", 1: "Q3_ERR_INVALID", 2: "Q3_ERR_CUDA", 3: "Q3_ERR_KV_OVERFLOW",

@@ -180,3 +180,12 @@ SPEC_MID = ModelSpec(name="mid", hidden=2048, inter=1024, layers=2, heads=4, kv_
                      cp_hidden=1024, cp_inter=1024, cp_layers=2, cp_heads=4, cp_kv_heads=2,
                      vocoder=TINY_VOCODER)
 SPECS["mid"] = SPEC_MID
+
+# "ring": the 1.7B's matrix shapes (hidden 2048, 16/8 heads, inter 6144; code predictor 1024 / 3072; small_to_mtp projection)
+# with 2 + 2 layers: every skinny-GEMM K is a multiple of 1024, so the TMA-ring kernel (mega4.cuh, Q3_MEGA=4) takes it --
+# K = 3072 and 6144 down projections, 48-row gate/up tiles, 16-token pass 0 -- and the CPU oracle still finishes in seconds.
+SPEC_RING = ModelSpec(name="ring", hidden=2048, inter=6144, layers=2, heads=16, kv_heads=8,
+                      text_vocab=2048, text_embed_dim=256,
+                      cp_hidden=1024, cp_inter=3072, cp_layers=2, cp_heads=16, cp_kv_heads=8,
+                      vocoder=TINY_VOCODER)
+SPECS["ring"] = SPEC_RING

@@ -245,13 +245,21 @@ def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
     dimensions exercise the register-resident, streaming and ring code paths (hidden 2048 / CP hidden 1024):
     free-running forks from the oracle only at near-ties, identical results on a second run, and across the
     16-frame launch boundary (40 frames = 3 launches, so the session's tag counter is carried between launches)."""
+    from qwen3_tts_rs_b200 import lib as L
+    if mega in ("1", "3") and not L.IS_DEV:
+        pytest.skip("historical generation: only in libq3tts_b200_dev.so (run with Q3TTS_LIB=dev)")
     monkeypatch.setenv("Q3_MEGA", mega)
-    spec = S.SPEC_MID
+    # generation 4 needs every skinny-GEMM K to be a multiple of 1024: SPEC_RING has the 1.7B's matrix shapes (K = 1024, 2048,
+    # 3072, 6144; 48-row gate/up tiles) with 2 + 2 layers; the others run the mid spec as in round 1
+    spec = S.SPEC_RING if mega == "4" else S.SPEC_MID
     B, F = 4, 40
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(10 + i, spec) for i in range(B)]
     seeds = [77 + i for i in range(B)]
     tts = gpu_tts(spec)
+    probe = api.Session(tts.model, B, opts, seeds)
+    assert probe.decode_generation() == int(mega), "the requested generation was replaced by a fallback"
+    probe.close()
     a = tts.generate_codes(prompts, options=opts, seeds=seeds)
     b = tts.generate_codes(prompts, options=opts, seeds=seeds)
     assert a == b

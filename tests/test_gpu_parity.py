@@ -18,8 +18,12 @@ Held at every frame of every followed row:
   3. acoustic codes == arg-max (lowest index among ties) of the CUDA path's own code-predictor logits -- bit-exact.
   4. talker input == bf16(bf16(sem + sum_i E_i[c_i]) + trailing_text_row_or_tts_pad) computed by the oracle from the
      emitted codes (lib.rs:612-622, code_predictor.rs:497-519) -- bit-exact (the trailing-text rule).
-  5. code-predictor logits, talker hidden-derived logits and prefill logits vs the oracle's, element-wise, with the
-     element-wise tolerance of tests/test_gpu_model.py (|d| <= 2^-6 |ref| + 2^-4 rms) and mean |d| <= 2^-6 rms.
+  5. code-predictor logits, talker logits and prefill logits against the oracle with a NOISE-CALIBRATED bar: the oracle
+     follows the same codes twice, in bf16 mode (the reference's CUDA-path arithmetic) and in f32 mode, and for every
+     tensor   rms(cuda - f32) <= 1.5 rms(bf16 - f32) + 1e-3 rms   and   max|cuda - f32| <= 8 rms(bf16 - f32) + 1e-2 rms,
+     i.e. the CUDA path must be as close to exact arithmetic as the reference's own bf16 rounding is (measured on B200,
+     tools/parity_noise.py: 1.02-1.08 at 1.7B where a fixed 2^-4 rms element bar fails on 0.1 % of the logits after 28
+     layers).  A wrong operand, position or rounding point shows up at the scale of rms itself, ~50x this bar.
   6. where the oracle's own arg-max differs from the emitted code, the oracle's top-2 margin is below 2^-5 |top1|.
 """
 import numpy as np
@@ -33,18 +37,17 @@ from helpers import gpu_tts, oracle_cfg, oracle_models
 pytestmark = pytest.mark.gpu
 
 
-def close_bf16(a, b, what):
-    """Element-wise bar of tests/test_gpu_model.py (|d| <= 2^-6 |ref| + 2^-4 rms); the bar on the MEAN error is 2^-6 rms here
-    (2 bf16 ulp at the tensor's rms) instead of 2^-7: in follow mode the two sides do not share inputs bit for bit -- the
-    code predictor reads the path's own talker hidden state and the KV caches hold the path's own keys and values, each a
-    bf16 ulp or two from the oracle's -- so the noise floor is one rounding step higher than in the teacher-forced test.
-    A wrong operand, position or rounding point shows up at the scale of rms itself (50x this bar)."""
-    a, b = torch.as_tensor(a).float().flatten(), torch.as_tensor(b).float().flatten()
-    rms = float(b.pow(2).mean().sqrt())
-    tol = 2.0 ** -6 * b.abs() + 2.0 ** -4 * rms
-    bad = ((a - b).abs() > tol)
-    assert not bool(bad.any()), f"{what}: {int(bad.sum())}/{a.numel()} outside tolerance, max |d|={float((a-b).abs().max()):.4g}, rms={rms:.4g}"
-    assert float((a - b).abs().mean()) <= 2.0 ** -6 * rms, f"{what}: mean |d| {float((a-b).abs().mean()):.4g} vs rms {rms:.4g}"
+def close_to_f32(cuda, bf, f32, what, stats):
+    """Item 5 of the module docstring for one tensor; `stats` collects the worst ratios for the report."""
+    cuda, bf, f32 = [torch.as_tensor(np.asarray(x, dtype=np.float32)).flatten() for x in (cuda, bf, f32)]
+    rms = float(f32.pow(2).mean().sqrt())
+    sigma = float((bf - f32).pow(2).mean().sqrt())
+    e_rms = float((cuda - f32).pow(2).mean().sqrt())
+    e_max = float((cuda - f32).abs().max())
+    stats["rms_ratio"] = max(stats.get("rms_ratio", 0.0), e_rms / max(sigma, 1e-12))
+    stats["max_over_sigma"] = max(stats.get("max_over_sigma", 0.0), e_max / max(sigma, 1e-12))
+    assert e_rms <= 1.5 * sigma + 1e-3 * rms, f"{what}: rms(cuda - f32) {e_rms:.4g} vs rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})"
+    assert e_max <= 8.0 * sigma + 1e-2 * rms, f"{what}: max|cuda - f32| {e_max:.4g} vs rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})"
 
 
 def run_tapped(tts, prompts, seeds, opts, frames):
@@ -57,12 +60,13 @@ def run_tapped(tts, prompts, seeds, opts, frames):
     return [codes[b, : n[b]].tolist() for b in range(len(prompts))], taps
 
 
-def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, taps=None, models=None):
+def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, taps=None, models=None, models32=None):
     """Runs the tapped CUDA loop (unless given) and holds rows `rows` to the oracle as the module docstring says.
     Returns a report dict (counts only; every violation asserts)."""
     if tapped is None:
         tapped, taps = run_tapped(tts, prompts, seeds, opts, frames)
     tk, cp = models if models is not None else oracle_models(spec)
+    tk32, cp32 = models32 if models32 is not None else oracle_models(spec, bf16=False)
     cfg = oracle_cfg(opts)
     rep = dict(rows=len(rows), frames=0, sampled=0, sample_exempt=0, codes=0, oracle_argmax_differs=0)
     for b in rows:
@@ -71,6 +75,8 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
         emb = tk.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
         fo = OG.follow(tk, cp, emb, prompts[b], cfg, seeds[b], got, first_logits=taps["first_logits"][b],
                        frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=frames + 64)
+        emb32 = tk32.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+        f32 = OG.follow(tk32, cp32, emb32, prompts[b], cfg, seeds[b], got, kv_max=frames + 64)      # noise calibration (item 5)
         # 1. RNG stream
         assert [int(x) for x in taps["rng"][: n + 1, b]] == fo["rng_states"], ("rng stream", b)
         # 2. sampler replay on the CUDA path's own logits
@@ -86,7 +92,7 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
             if fo["replayed"][f] != expect:
                 assert fo["margins"][f] is not None and fo["margins"][f] <= 2e-6, ("sampled token", b, f, fo["replayed"][f], expect, fo["margins"][f])
                 rep["sample_exempt"] += 1
-        close_bf16(taps["first_logits"][b], fo["prefill_logits"], f"prefill logits row {b}")
+        close_to_f32(taps["first_logits"][b], fo["prefill_logits"], f32["prefill_logits"], f"prefill logits row {b}", rep)
         for f in range(n):
             o = fo["frames"][f]
             # 3. greedy codes are the arg-max of the path's own logits
@@ -97,8 +103,10 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
             assert torch.equal(taps["step_input"][f, b].view(torch.int16),
                                o["step_input"][0, 0].to(torch.bfloat16).view(torch.int16)), ("step_input", b, f)
             # 5. tensors vs the oracle
-            close_bf16(taps["cp_logits"][f, :, b], o["cp_logits"], f"cp logits row {b} frame {f}")
-            close_bf16(taps["logits"][f, b], o["logits"], f"talker logits row {b} frame {f}")
+            o32 = f32["frames"][f]
+            close_to_f32(taps["cp_logits"][f, :, b], o["cp_logits"].float().numpy(), o32["cp_logits"].float().numpy(),
+                         f"cp logits row {b} frame {f}", rep)
+            close_to_f32(taps["logits"][f, b], o["logits"], o32["logits"], f"talker logits row {b} frame {f}", rep)
             # 6. the oracle's own arg-max
             for g in range(15):
                 if o["own_codes"][g] != got[f][1 + g]:
@@ -110,15 +118,23 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
     return rep
 
 
-@pytest.mark.parametrize("spec", [S.SPEC_TINY, S.SPEC_TINY_PROJ, S.SPEC_MID], ids=lambda s: s.name)
-def test_free_running_generate_follows_the_oracle_every_frame(spec):
+@pytest.mark.parametrize("spec,mega", [(S.SPEC_TINY, None), (S.SPEC_TINY_PROJ, None), (S.SPEC_MID, None), (S.SPEC_RING, None),
+                                       (S.SPEC_RING, "4")], ids=["tiny", "tiny_proj", "mid", "ring", "ring-mega4"])
+def test_free_running_generate_follows_the_oracle_every_frame(spec, mega, monkeypatch):
     """64 frames, batch 8 (4 launches of 16 frames in the production path): tapped run == untapped run bit for bit, and
-    three rows are held to the oracle at every frame (module docstring, items 1-6)."""
+    three rows are held to the oracle at every frame (module docstring, items 1-6).  "ring" has the 1.7B's matrix shapes
+    with 2 + 2 layers; "ring-mega4" runs it on the TMA-ring generation of the persistent kernel (Q3_MEGA=4)."""
+    if mega is not None:
+        monkeypatch.setenv("Q3_MEGA", mega)
     B, F = 8, 64
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(200 + i, spec) for i in range(B)]
     seeds = [4242 + i for i in range(B)]
     tts = gpu_tts(spec)
+    if mega is not None:
+        probe = api.Session(tts.model, B, opts, seeds)
+        assert probe.decode_generation() == int(mega), "the requested generation was replaced by a fallback"
+        probe.close()
     plain = tts.generate_codes(prompts, options=opts, seeds=seeds)
     tapped, taps = run_tapped(tts, prompts, seeds, opts, F)
     assert tapped == plain                       # one frame per launch == 16 frames per launch, bit-identical
@@ -128,12 +144,15 @@ def test_free_running_generate_follows_the_oracle_every_frame(spec):
     assert rep["oracle_argmax_differs"] <= rep["codes"] // 50       # near-ties are rare (2048-way arg-max)
 
 
-@pytest.mark.parametrize("spec,batch", [(S.SPEC_1_7B, 8), (S.SPEC_1_7B, 1), (S.SPEC_0_6B, 8)], ids=["1.7b-b8", "1.7b-b1", "0.6b-b8"])
-def test_baseline_dimensions_follow_the_oracle(spec, batch):
+@pytest.mark.parametrize("spec,batch,mega", [(S.SPEC_1_7B, 8, None), (S.SPEC_1_7B, 1, None), (S.SPEC_0_6B, 8, None), (S.SPEC_1_7B, 8, "4")],
+                         ids=["1.7b-b8", "1.7b-b1", "0.6b-b8", "1.7b-b8-mega4"])
+def test_baseline_dimensions_follow_the_oracle(spec, batch, mega, monkeypatch):
     """BASELINE.json's model dimensions (1.7B: hidden 2048, 28 layers, 16/8 heads, inter 6144, small_to_mtp projection;
     0.6B: hidden 1024, inter 3072, no projection), batch 8 and batch 1, 3 frames: the same six checks, i.e. the K = 6144
     down-projection, the 16/8-head GQA mapping, 28-layer error growth and the register-resident vs streaming kernel
     variants at their real sizes are compared with the oracle, through the production loop."""
+    if mega is not None:
+        monkeypatch.setenv("Q3_MEGA", mega)
     F = 3
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(i, spec) for i in range(batch)]
@@ -146,6 +165,27 @@ def test_baseline_dimensions_follow_the_oracle(spec, batch):
     rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=rows, tapped=tapped, taps=taps)
     print("follow report:", rep)
     assert rep["frames"] == len(rows) * F and rep["sample_exempt"] == 0
+
+
+@pytest.mark.parametrize("mega", ["2", "4"])
+def test_code_predictor_frame_repeats_bit_for_bit_at_1p7b(mega, monkeypatch):
+    """Race detector at BASELINE dimensions: the code-predictor frame (405 dependent phases of the persistent kernel, one
+    launch) run 150 times on identical inputs must give bit-identical logits every time, on both generations.  (This is the
+    test that caught the early slot release of the TMA-ring kernel: mbarrier.arrive scheduled ahead of the MMAs that consume
+    the slot's fragments, 73 of 300 repetitions differed at batch 8; tools/cp_repeat.py, tools/cp_bisect.py.)"""
+    monkeypatch.setenv("Q3_MEGA", mega)
+    spec, B = S.SPEC_1_7B, 8
+    tts = gpu_tts(spec)
+    sess = api.Session(tts.model, B, api.SynthesisOptions(max_length=64), list(range(B)), max_seq=128)
+    assert sess.decode_generation() == int(mega)
+    g = torch.Generator().manual_seed(5)
+    hid = (torch.randn(B, spec.hidden, generator=g) * 0.7).to(torch.bfloat16)
+    toks = [100 + 37 * i for i in range(B)]
+    ref_codes, ref = sess.code_predictor_frame(hid, toks, want_logits=True)
+    for it in range(150):
+        codes, lg = sess.code_predictor_frame(hid, toks, want_logits=True)
+        assert np.array_equal(lg, ref) and np.array_equal(codes, ref_codes), ("repetition differs", it)
+    sess.close()
 
 
 def test_eos_row_follows_the_oracle_to_its_last_frame():
@@ -169,5 +209,6 @@ def test_eos_row_follows_the_oracle_to_its_last_frame():
     assert [len(r) for r in tapped] == [2, 2]
     # follow with the modified weights
     models = (OM.Talker(spec, w, OM.BF16P), OM.CodePredictor(spec, w, OM.BF16P))
-    rep = check_follow(spec, tts, prompts, seeds, opts, 12, rows=(0, 1), tapped=tapped, taps=taps, models=models)
+    models32 = (OM.Talker(spec, w, OM.F32P), OM.CodePredictor(spec, w, OM.F32P))
+    rep = check_follow(spec, tts, prompts, seeds, opts, 12, rows=(0, 1), tapped=tapped, taps=taps, models=models, models32=models32)
     assert rep["sampled"] == 2 * 3 and rep["sample_exempt"] == 0      # first token, token after frame 0, EOS after frame 1

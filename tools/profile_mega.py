@@ -1,5 +1,6 @@
 """Timestamp breakdown of the persistent frame kernel (block 0): stage / tiles / barrier per phase."""
 import os, sys, ctypes as C
+os.environ.setdefault("Q3TTS_LIB", "dev")      # profiling hooks live in the development library
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from qwen3_tts_rs_b200 import api, lib as L, spec as S, weights as W
