@@ -343,14 +343,15 @@ def main():
     vw = W.make_vocoder_weights(spec.vocoder)
     tts = api.Qwen3TTS.from_weights(spec, tw, vw, device=local_rank)
     lib = L.load()
-    kernel = {4: "decode_frames_mega4_kernel", 3: "decode_frames_mega3_kernel", 1: "decode_frames_mega_kernel"}.get(
-        int(os.environ.get("Q3_MEGA", "4") or 4), "decode_frames_mega2_kernel")
+    kernel = None      # set from the session once it exists (which generation of the persistent kernel actually runs)
     peak, peak_src = measured_peaks()
     B, F = args.batch, args.frames
     warm = max(args.warmup, 3)
 
     # ---- headline: weak scaling, B utterances per GPU ------------------------------------------------
     leg = Leg(tts, spec, lib, B, F, rank * B, local_rank)
+    kernel = {0: "multi-kernel CUDA graph (gemv_kernel ...)", 1: "decode_frames_mega_kernel", 2: "decode_frames_mega2_kernel",
+              3: "decode_frames_mega3_kernel", 4: "decode_frames_mega4_kernel"}[leg.sess.decode_generation()]
     m = measure(leg, args.steps, warm, rank, world, B * world, want_clocks=True, local_rank=local_rank)
     lmax = leg.lmax
     leg.close()

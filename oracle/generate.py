@@ -128,7 +128,7 @@ def prefill_and_generate(talker: Talker, cp: CodePredictor, prefill_embeds: torc
 def follow(talker: Talker, cp: CodePredictor, prefill_embeds: torch.Tensor, text_ids: Sequence[int],
            cfg: smp.GenerationConfig, seed: int, frames: Sequence[Sequence[int]],
            first_logits: Optional[np.ndarray] = None, frame_logits: Optional[Sequence[np.ndarray]] = None,
-           kv_max: Optional[int] = None) -> dict:
+           kv_max: Optional[int] = None, text_rows=None) -> dict:
     """Test aid (no reference counterpart): the loop of generate_codes (lib.rs:530-656) FOLLOWING a trajectory produced
     elsewhere.  `frames[f] = [tok, c0..c14]` are the codes the CUDA path emitted; every decision input (semantic token,
     acoustic codes fed to the next code-predictor pass, penalty mask) is taken from them, every tensor is this oracle's
@@ -147,12 +147,19 @@ def follow(talker: Talker, cp: CodePredictor, prefill_embeds: torch.Tensor, text
     penalty_mask = np.zeros((1, vocab), dtype=np.float32)
     ctx = smp.SamplingContext(seed)
     trailing, tlen, pad = talker.build_trailing_text(text_ids)
+    out_text = dict(trailing=trailing.clone(), pad=pad.clone())
+    if text_rows is not None:
+        # (trailing [1, tlen, H], pad [1, 1, H]) as the OTHER side projected them: the talker-input add (lib.rs:617-621) is then
+        # checked bit-exactly on its own, without inheriting the rounding noise of the text-projection GEMM
+        tr_o, pad_o = text_rows
+        assert tr_o.shape[1] == tlen, (tr_o.shape, tlen)
+        trailing, pad = tr_o.to(torch.float32), pad_o.to(torch.float32)
     caches = talker.new_kv_caches(kv_max if kv_max is not None else cfg.max_new_tokens + 256)
     hidden, logits = talker.run_prefill_layers(prefill_embeds, caches)
     offset = hidden.shape[1]
     last_hidden = hidden[:, offset - 1: offset]
     cp_caches = cp.new_kv_caches()
-    out = dict(prefill_logits=logits[:, 0].numpy().astype(np.float32)[0], frames=[], replayed=[], margins=[], rng_states=[])
+    out = dict(text=out_text, prefill_logits=logits[:, 0].numpy().astype(np.float32)[0], frames=[], replayed=[], margins=[], rng_states=[])
 
     def replay(raw, token_count):
         l2 = smp.apply_generation_penalties(np.asarray(raw, dtype=np.float32)[None], penalty_mask, cfg, token_count, suppression)

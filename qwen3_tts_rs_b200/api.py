@@ -239,6 +239,18 @@ class Session:
         L.check(self.lib.q3_generate(self.handle, max_frames, _ptr(codes), _ptr(n)))
         return codes, n
 
+    def trailing_rows(self, cap: int = 256):
+        """q3_debug_get_trailing (test aid): (trailing bf16 [B, cap, H], lt [B], tts_pad bf16 [H]) as built on the device."""
+        H = self.model.spec.hidden
+        tr = torch.zeros(self.B, cap, H, dtype=torch.bfloat16)
+        lt = np.zeros(self.B, dtype=np.int32)
+        pad = torch.zeros(H, dtype=torch.bfloat16)
+        fn = self.lib.q3_debug_get_trailing
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+        L.check(fn(self.handle, _ptr(tr), cap, _ptr(lt), _ptr(pad)))
+        return tr, lt, pad
+
     def decode_generation(self) -> int:
         """0 = multi-kernel CUDA graph, 1..4 = generation of the persistent frame kernel this session runs on (debug aid)."""
         fn = self.lib.q3_debug_decode_generation

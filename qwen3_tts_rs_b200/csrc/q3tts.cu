@@ -1734,6 +1734,23 @@ q3_status q3_debug_generate_tapped(q3_session* s, int32_t max_frames, uint32_t* 
   Q3_API_END
 }
 
+// Test aid: the session's trailing-text rows as the DEVICE built them (q3_set_trailing_ids: text projection GEMM) -- the
+// second operand of the talker-input add (lib.rs:617-621) -- so a test can check that add bit-exactly without inheriting the
+// rounding noise of the projection.  trailing: bf16 [B][cap][H] (rows past lt[b] untouched), lt: [B], tts_pad: bf16 [H].
+q3_status q3_debug_get_trailing(q3_session* s, uint16_t* trailing, int32_t cap, int32_t* lt, uint16_t* tts_pad) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && trailing && lt && tts_pad && cap >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const size_t H = s->m->d.hidden;
+  const int rows = std::min(cap, s->lt_max);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(lt, s->lt.p, s->B * 4, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(tts_pad, s->tts_pad.p, H * 2, cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaMemcpy2DAsync(trailing, (size_t)cap * H * 2, s->fs.trailing, (size_t)s->lt_max * H * 2, (size_t)rows * H * 2, s->B,
+                                  cudaMemcpyDeviceToHost, s->st));
+  Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+  Q3_API_END
+}
+
 // Debug aid: which decode engine the session runs on: 0 = multi-kernel CUDA graph, 1 / 2 / 3 / 4 = generation of the persistent
 // frame kernel (mega.cuh, mega2.cuh, mega3.cuh, mega4.cuh).  Tests use it to make sure a requested generation was not silently
 // replaced by a fallback.

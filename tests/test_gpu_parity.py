@@ -17,10 +17,13 @@ Held at every frame of every followed row:
      tests); exemptions are counted and must be zero in practice.
   3. acoustic codes == arg-max (lowest index among ties) of the CUDA path's own code-predictor logits -- bit-exact.
   4. talker input == bf16(bf16(sem + sum_i E_i[c_i]) + trailing_text_row_or_tts_pad) computed by the oracle from the
-     emitted codes (lib.rs:612-622, code_predictor.rs:497-519) -- bit-exact (the trailing-text rule).
+     emitted codes (lib.rs:612-622, code_predictor.rs:497-519) -- bit-exact (the trailing-text rule: row
+     frame_idx while frame_idx < trailing length, tts_pad after).  The text rows are the ones the device projected
+     (q3_debug_get_trailing), themselves held to the oracle's projection by the bar of item 5, so that a one-ulp
+     difference of the projection GEMM does not mask -- or fake -- an error of the add.
   5. code-predictor logits, talker logits and prefill logits against the oracle with a NOISE-CALIBRATED bar: the oracle
      follows the same codes twice, in bf16 mode (the reference's CUDA-path arithmetic) and in f32 mode, and for every
-     tensor   rms(cuda - f32) <= 1.5 rms(bf16 - f32) + 1e-3 rms   and   max|cuda - f32| <= 8 rms(bf16 - f32) + 1e-2 rms,
+     tensor   rms(cuda - f32) <= 1.5 rms(bf16 - f32) + 1e-3 rms   and   |cuda - f32| <= 8 rms(bf16 - f32) + 1e-2 rms + 2^-6 |f32|,
      i.e. the CUDA path must be as close to exact arithmetic as the reference's own bf16 rounding is (measured on B200,
      tools/parity_noise.py: 1.02-1.08 at 1.7B where a fixed 2^-4 rms element bar fails on 0.1 % of the logits after 28
      layers).  A wrong operand, position or rounding point shows up at the scale of rms itself, ~50x this bar.
@@ -47,14 +50,19 @@ def close_to_f32(cuda, bf, f32, what, stats):
     stats["rms_ratio"] = max(stats.get("rms_ratio", 0.0), e_rms / max(sigma, 1e-12))
     stats["max_over_sigma"] = max(stats.get("max_over_sigma", 0.0), e_max / max(sigma, 1e-12))
     assert e_rms <= 1.5 * sigma + 1e-3 * rms, f"{what}: rms(cuda - f32) {e_rms:.4g} vs rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})"
-    assert e_max <= 8.0 * sigma + 1e-2 * rms, f"{what}: max|cuda - f32| {e_max:.4g} vs rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})"
+    # element-wise: 8 sigma + 1 % of rms + 4 bf16 ulp of the element itself (a logit of magnitude 60 has a bf16 ulp of 0.25)
+    over = (cuda - f32).abs() - (8.0 * sigma + 1e-2 * rms + 2.0 ** -6 * f32.abs())
+    assert float(over.max()) <= 0.0, (f"{what}: {int((over > 0).sum())}/{over.numel()} elements outside the bar, max|cuda - f32| {e_max:.4g} vs "
+                                      f"rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})")
 
 
 def run_tapped(tts, prompts, seeds, opts, frames):
     pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
     sess = tts._new_session(prompts, pp, opts, seeds)
     try:
+        text = sess.trailing_rows(cap=max(len(t) for t in prompts) + 1)
         codes, n, taps = sess.generate_tapped(frames)
+        taps["text"] = text
     finally:
         sess.close()
     return [codes[b, : n[b]].tolist() for b in range(len(prompts))], taps
@@ -73,8 +81,15 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
         got = tapped[b]
         n = len(got)
         emb = tk.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+        tr_rows, tr_lt, tr_pad = taps["text"]
+        gpu_text = (tr_rows[b, : int(tr_lt[b])][None], tr_pad[None, None])
         fo = OG.follow(tk, cp, emb, prompts[b], cfg, seeds[b], got, first_logits=taps["first_logits"][b],
-                       frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=frames + 64)
+                       frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=frames + 64, text_rows=gpu_text)
+        # the device's text projection (trailing rows + tts_pad) vs the oracle's: the same noise-calibrated bar as the logits
+        o_tr = torch.cat([fo["text"]["trailing"][0], fo["text"]["pad"][0]], 0)
+        g_tr = torch.cat([gpu_text[0][0].float(), gpu_text[1][0].float()], 0)
+        f_tr32, f_len, f_pad32 = tk32.build_trailing_text(prompts[b])
+        close_to_f32(g_tr, o_tr, torch.cat([f_tr32[0], f_pad32[0]], 0), f"trailing text rows row {b}", rep)
         emb32 = tk32.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
         f32 = OG.follow(tk32, cp32, emb32, prompts[b], cfg, seeds[b], got, kv_max=frames + 64)      # noise calibration (item 5)
         # 1. RNG stream
@@ -141,7 +156,7 @@ def test_free_running_generate_follows_the_oracle_every_frame(spec, mega, monkey
     rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=(0, 3, 7), tapped=tapped, taps=taps)
     print("follow report:", rep)
     assert rep["frames"] == 3 * F and rep["sample_exempt"] == 0
-    assert rep["oracle_argmax_differs"] <= rep["codes"] // 50       # near-ties are rare (2048-way arg-max)
+    assert rep["oracle_argmax_differs"] <= rep["codes"] // 20       # near-ties (each one verified above) stay a small minority
 
 
 @pytest.mark.parametrize("spec,batch,mega", [(S.SPEC_1_7B, 8, None), (S.SPEC_1_7B, 1, None), (S.SPEC_0_6B, 8, None), (S.SPEC_1_7B, 8, "4")],
