@@ -140,10 +140,14 @@ q3_status q3_get_codes(q3_session* s, int32_t max_frames, uint32_t* codes, int32
  * *done != 0 when every row has finished and nothing is buffered. */
 q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_frames, int32_t* done);
 /* Opt-in extension (no reference counterpart -- the reference decodes every chunk without left
- * context, src/lib.rs:1755-1758, so streamed PCM differs from non-streamed PCM at chunk starts).  With
- * left_context_frames = c > 0 each q3_stream_next decodes the previous min(c, frames so far) frames again in front of the
- * chunk and drops their samples; every vocoder op is causal, so c < 0 (= the whole history) makes the streamed PCM
- * identical to q3_vocode_session's, and a finite c bounds the extra work per chunk.  0 (default) = reference behaviour. */
+ * context, src/lib.rs:1755-1758, so streamed PCM differs from non-streamed PCM at chunk starts).
+ *   left_context_frames  = 0 (default): the reference's stateless chunks.
+ *   left_context_frames  < 0: STATEFUL streaming.  The session carries the vocoder's cross-chunk state (keys / values of the
+ *     pre-transformer for every frame so far, and the last 10 frames of the conv stack's input, whose look-back is 9.4
+ *     frames), so every q3_stream_next costs O(chunk + 10 frames) of vocoder work however long the utterance is, and the
+ *     streamed PCM is identical to q3_vocode_session's (every vocoder op is causal).  Any chunk size >= 1 frame.
+ *   left_context_frames  = c > 0: re-decode form -- the previous min(c, frames so far) frames are decoded again in front of
+ *     the chunk and their samples dropped; approximate for finite c (the pre-transformer sees only c frames of history). */
 q3_status q3_session_set_stream_context(q3_session* s, int32_t left_context_frames);
 
 /* ref: Decoder12Hz::decode (src/models/codec/decoder_12hz.rs:411-505).  codes: i64 [B][16][T]

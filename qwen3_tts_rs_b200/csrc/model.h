@@ -108,6 +108,16 @@ struct VocoderWorkspace {
   DBuf codes, e_first, e_rest, a, b, c, d, qh, kh, vh;
 };
 
+// Carried state of a STATEFUL streamed decode (q3_session_set_stream_context(sess, -1)): keys and values
+// of the pre-transformer for every frame decoded so far, and the front half's output (the input of the causal conv stack),
+// of which the back half needs the last 10 frames as left context (its look-back is 9.4 frames).
+struct VocoderStreamState {
+  DBuf kc, vc;        // [layers][B][heads][cap][head_dim] f32
+  DBuf front;         // [B][latent][cap] f32, channel-major
+  DBuf win;           // [B][latent][<= 10 + chunk] staging of the back half's input window
+  int cap = 0, frames = 0;
+};
+
 // Vocoder scratch of one session (multi-GB at 256 frames x 8 rows).  Sessions borrow it from the model's pool and hand
 // it back when they are destroyed: a cudaMalloc + cudaFree of these buffers per synthesize call cost ~0.7 s.
 struct VocoderScratch {
@@ -160,6 +170,14 @@ void vocoder_finalize(q3_model* m);
 // codes: device i64 [B][nq][T]; pcm: device f32 [B][T*upsample]
 void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes, int B, int T, float* pcm,
                  cudaStream_t st);
+// Streamed chunk [f0, f0 + T) of every row, stateful: front half over the new frames with the carried keys / values (exact:
+// the pre-transformer attends to the whole history), back half over the chunk and the min(10, f0) frames before it.
+// codes_win: device i64 [B][nq][c0 + T] for frames [f0 - c0, f0 + T), c0 = min(2, f0) (left context of the k = 3 pre-conv).
+// pcm: device f32 [B][(cb + T) * upsample] with cb = min(10, f0): the caller drops the first cb * upsample samples of a row.
+void vocoder_stream_chunk(const q3_model* m, VocoderWorkspace& ws, VocoderStreamState& ss, const long long* codes_win, int B,
+                          int f0, int T, float* pcm, cudaStream_t st);
+constexpr int VOC_STREAM_BACK_CTX = 10;
+constexpr int VOC_STREAM_FRONT_CTX = 2;
 int vocoder_total_upsample(const q3_model* m);
 // u32 frame-major codes [B][frames_cap][16] -> i64 [B][16][T] starting at frame f0 (codes_to_tensor, lib.rs:1417-1431)
 void vocoder_codes_to_tensor(const uint32_t* frames, int frames_cap, int f0, int T, int B, long long* out, cudaStream_t st);

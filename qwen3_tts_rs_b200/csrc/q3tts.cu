@@ -78,6 +78,7 @@ struct q3_session {
   std::vector<int> stream_emitted;
   int stream_left_ctx = 0;         // frames of left context re-decoded per chunk (0 = the reference's stateless chunks)
   std::unique_ptr<VocoderScratch> voc;   // borrowed from the model's pool at the first vocode, returned on destruction
+  std::unique_ptr<VocoderStreamState> vstream;   // carried vocoder state of a stateful streamed decode (stream context -1)
   // timing
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_poll[2] = {nullptr, nullptr};
   q3_timing timing{};
@@ -1040,6 +1041,7 @@ static void reset_state(q3_session* s, const uint64_t* seeds) {
   }
   std::fill(s->prefill_len.begin(), s->prefill_len.end(), 0);
   std::fill(s->stream_emitted.begin(), s->stream_emitted.end(), 0);
+  if (s->vstream) s->vstream->frames = 0;
 }
 
 q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, const q3_gen_config* cfg,
@@ -1437,6 +1439,48 @@ static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& ro
   }
 }
 
+// Stateful streamed decode of frames [f0, f0+T) (q3_session_set_stream_context(sess, -1)): the pre-transformer's keys / values
+// and the front half's outputs are carried in the session, so a chunk costs O(chunk + 10 frames) of vocoder work however long
+// the utterance is, and the samples equal the ones a single decode of the whole utterance produces (every op is causal; the
+// conv stack looks back 9.4 frames).  No reference counterpart: lib.rs:1755-1758 decodes chunks statelessly.
+static void vocode_rows_stateful(q3_session* s, int f0, int T, const std::vector<int>& row_len, float* pcm_host, size_t pcm_row_stride) {
+  const q3_model* m = s->m;
+  const q3_model_desc& d = m->d;
+  const int B = s->B, up = vocoder_total_upsample(m);
+  if (T <= 0) return;
+  if (!s->voc) s->voc = m->acquire_scratch();
+  if (!s->vstream) {
+    s->vstream.reset(new VocoderStreamState());
+    VocoderStreamState& ss = *s->vstream;
+    ss.cap = std::min(s->frames_cap, 3072);
+    const size_t kv = (size_t)d.v_layers * B * d.v_heads * ss.cap * d.v_head_dim * sizeof(float);
+    ss.kc.alloc(kv); ss.vc.alloc(kv);
+    ss.front.alloc((size_t)B * d.v_latent_dim * ss.cap * sizeof(float));
+  }
+  VocoderStreamState& ss = *s->vstream;
+  Q3_REQUIRE(f0 == ss.frames, Q3_ERR_STATE, "stateful streaming: chunks must be decoded in order");
+  const int c0 = std::min((int)VOC_STREAM_FRONT_CTX, f0), Tw = c0 + T;
+  const int cb = std::min((int)VOC_STREAM_BACK_CTX, f0), Tb = cb + T;
+  DBuf& voc_codes = s->voc->codes;
+  DBuf& voc_pcm = s->voc->pcm;
+  voc_codes.ensure((size_t)B * 16 * Tw * 8);
+  voc_pcm.ensure((size_t)B * Tb * up * 4);
+  vocoder_codes_to_tensor(s->codes.as<uint32_t>(), s->frames_cap, f0 - c0, Tw, B, voc_codes.as<long long>(), s->st);
+  vocoder_stream_chunk(m, s->voc->ws, ss, voc_codes.as<long long>(), B, f0, T, voc_pcm.as<float>(), s->st);
+  if (pcm_host) {
+    for (int b = 0; b < B; ++b) {
+      const size_t n = (size_t)row_len[b] * up;
+      if (n) Q3_CHECK_CUDA(cudaMemcpyAsync(pcm_host + b * pcm_row_stride, voc_pcm.as<float>() + ((size_t)b * Tb + cb) * up, n * 4,
+                                           cudaMemcpyDeviceToHost, s->st));
+    }
+    Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
+    for (int b = 0; b < B; ++b) {
+      const size_t n = (size_t)row_len[b] * up;
+      if (n < (size_t)T * up) memset(pcm_host + b * pcm_row_stride + n, 0, ((size_t)T * up - n) * 4);
+    }
+  }
+}
+
 q3_status q3_session_set_stream_context(q3_session* s, int32_t left_context_frames) {
   Q3_API_BEGIN
   Q3_REQUIRE(s, Q3_ERR_INVALID, "null session");
@@ -1497,7 +1541,8 @@ q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_
     for (int b = 0; b < B; ++b)
       if (len[b] > 0) { if (f0 < 0) f0 = s->stream_emitted[b]; else same = same && (f0 == s->stream_emitted[b]); }
     Q3_REQUIRE(same, Q3_ERR_STATE, "streaming rows out of step");
-    vocode_rows(s, f0, T, len, pcm, (size_t)chunk * up, s->stream_left_ctx);
+    if (s->stream_left_ctx == INT32_MAX && s->frames_cap <= 3072) vocode_rows_stateful(s, f0, T, len, pcm, (size_t)chunk * up);
+    else vocode_rows(s, f0, T, len, pcm, (size_t)chunk * up, s->stream_left_ctx);
     for (int b = 0; b < B; ++b)
       if (len[b] > 0)
         Q3_CHECK_CUDA(cudaMemcpyAsync(codes + (size_t)b * chunk * 16, s->codes.as<uint32_t>() + ((size_t)b * s->frames_cap + f0) * 16,

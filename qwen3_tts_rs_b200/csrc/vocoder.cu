@@ -325,12 +325,12 @@ static size_t vocoder_max_act(const q3_model* m, int T) {
   return mx;
 }
 
-void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes, int B, int T, float* pcm, cudaStream_t st) {
-  Q3_REQUIRE(m->has_vocoder, Q3_ERR_STATE, "vocoder weights were not loaded");
-  if (B <= 0 || T <= 0) return;
+namespace {
+
+struct VocBufs { float *A, *Bf, *C, *D; };
+
+VocBufs voc_ensure(const q3_model* m, VocoderWorkspace& ws, int B, int T) {
   const q3_model_desc& d = m->d;
-  const VocoderW& v = m->voc;
-  Q3_REQUIRE(T <= 3072, Q3_ERR_UNSUPPORTED, "vocoder: at most 3072 frames per call");
   const size_t act = vocoder_max_act(m, T) * (size_t)B * sizeof(float);
   ws.a.ensure(act); ws.b.ensure(act); ws.c.ensure(act); ws.d.ensure(act);
   const int AD = d.v_heads * d.v_head_dim;
@@ -339,34 +339,56 @@ void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes
   ws.qh.ensure((size_t)B * AD * T * sizeof(float));
   ws.kh.ensure((size_t)B * AD * T * sizeof(float));
   ws.vh.ensure((size_t)B * AD * T * sizeof(float));
-  float *A = ws.a.as<float>(), *Bf = ws.b.as<float>(), *C = ws.c.as<float>(), *D = ws.d.as<float>();
+  return {ws.a.as<float>(), ws.b.as<float>(), ws.c.as<float>(), ws.d.as<float>()};
+}
 
-  // 1. RVQ decode: first_proj(E_first) + rest_proj(sum E_rest)   (decoder_12hz.rs:420-450)
+// RVQ decode + pre_conv + input projection over T frames: codes -> out [B][hidden][T]   (decoder_12hz.rs:420-470)
+void voc_embed(const q3_model* m, VocoderWorkspace& ws, const VocBufs& w, const long long* codes, int B, int T, float* out,
+               cudaStream_t st) {
+  const q3_model_desc& d = m->d;
+  const VocoderW& v = m->voc;
+  // 1. RVQ decode: first_proj(E_first) + rest_proj(sum E_rest)
   voc_rvq_gather_kernel<<<dim3(T, B), 128, 0, st>>>(codes, v.first_cb, v.rest_cb, d.v_quantizers, d.v_codebook_size,
                                                    d.v_vq_dim, T, ws.e_first.as<float>(), ws.e_rest.as<float>());
   Q3_COUNT_LAUNCH();
   Q3_LAUNCH_CHECK();
-  launch_conv(v.first_proj, ws.e_first.as<float>(), A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
-  launch_conv(v.rest_proj, ws.e_rest.as<float>(), Bf, B, T, 1, nullptr, A, nullptr, CEPI_NONE, st);   // Bf = A + rest
-  // 2. pre_conv (k3) -> C ; 3. input_proj -> A (hidden 512)
-  launch_conv(v.pre_conv, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
-  launch_conv(v.in_proj, C, A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
-  // transformer layers (decoder_12hz.rs:586-672); hidden lives in A
+  launch_conv(v.first_proj, ws.e_first.as<float>(), w.A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  launch_conv(v.rest_proj, ws.e_rest.as<float>(), w.Bf, B, T, 1, nullptr, w.A, nullptr, CEPI_NONE, st);   // Bf = A + rest
+  // 2. pre_conv (k3) -> C ; 3. input_proj -> out (hidden 512)
+  launch_conv(v.pre_conv, w.Bf, w.C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  launch_conv(v.in_proj, w.C, out, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+}
+
+// Pre-transformer (decoder_12hz.rs:586-672) over T frames whose first sits at position pos0; hidden lives in A and the result
+// of the output projection ([B][latent][T]) ends up in A.  kc / vc == nullptr: keys / values of this call only (whole
+// utterance, pos0 == 0); else the session's caches [layers][B][heads][cap][head_dim], to which this call appends.
+void voc_transformer(const q3_model* m, VocoderWorkspace& ws, const VocBufs& w, int B, int T, int pos0, float* kc, float* vc,
+                     int cap, cudaStream_t st) {
+  const q3_model_desc& d = m->d;
+  const VocoderW& v = m->voc;
+  float *A = w.A, *Bf = w.Bf, *C = w.C, *D = w.D;
   const float scale = 1.0f / sqrtf((float)d.v_head_dim);
-  Q3_REQUIRE((size_t)4 * T * sizeof(float) <= 48 * 1024, Q3_ERR_UNSUPPORTED, "vocoder attention: T too large");
+  const int Ltot = pos0 + T;
+  Q3_REQUIRE((size_t)4 * Ltot * sizeof(float) <= 48 * 1024, Q3_ERR_UNSUPPORTED, "vocoder attention: more than 3072 frames");
+  const size_t layer_stride = (size_t)B * d.v_heads * cap * d.v_head_dim;
+  int li = 0;
   for (const VLayer& L : v.layers) {
+    float* kdst = kc ? kc + (size_t)li * layer_stride : ws.kh.as<float>();
+    float* vdst = vc ? vc + (size_t)li * layer_stride : ws.vh.as<float>();
+    const int Tk = kc ? cap : T, to0 = kc ? pos0 : 0;
+    ++li;
     launch_norm(A, L.in_ln, nullptr, Bf, B, d.v_hidden, T, d.v_rms_eps, 0, st);
     launch_conv(L.q, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
-    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.qh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 1);
+    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.qh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 1, pos0, T, 0);
     Q3_COUNT_LAUNCH();
     launch_conv(L.k, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
-    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.kh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 1);
+    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, kdst, d.v_heads, d.v_head_dim, T, d.v_rope_theta, 1, pos0, Tk, to0);
     Q3_COUNT_LAUNCH();
     launch_conv(L.v, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
-    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, ws.vh.as<float>(), d.v_heads, d.v_head_dim, T, d.v_rope_theta, 0);
+    voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, vdst, d.v_heads, d.v_head_dim, T, d.v_rope_theta, 0, pos0, Tk, to0);
     Q3_COUNT_LAUNCH();
-    voc_attn_kernel<<<dim3(ceil_div(T, 4), d.v_heads, B), 128, (size_t)4 * T * sizeof(float), st>>>(
-        ws.qh.as<float>(), ws.kh.as<float>(), ws.vh.as<float>(), C, d.v_heads, d.v_head_dim, T, scale);
+    voc_attn_kernel<<<dim3(ceil_div(T, 4), d.v_heads, B), 128, (size_t)4 * Ltot * sizeof(float), st>>>(
+        ws.qh.as<float>(), kdst, vdst, C, d.v_heads, d.v_head_dim, T, scale, Tk, pos0);
     Q3_COUNT_LAUNCH();
     Q3_LAUNCH_CHECK();
     launch_conv(L.o, C, D, B, T, 1, nullptr, A, L.attn_scale, CEPI_NONE, st);        // D = A + scale*o_proj
@@ -382,13 +404,18 @@ void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes
     launch_conv(L.down, C, A, B, T, 1, nullptr, D, L.mlp_scale, CEPI_NONE, st);      // A = D + scale*down
   }
   launch_norm(A, v.final_norm, nullptr, Bf, B, d.v_hidden, T, d.v_rms_eps, 0, st);
-  launch_conv(v.out_proj, Bf, A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);   // [B][1024][T]
-  // upsample stages: transconv + ConvNeXt
+  launch_conv(v.out_proj, Bf, A, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);   // [B][latent][T]
+}
+
+// Back half: upsample stages (transposed conv + ConvNeXt), decoder blocks, final conv; input w.A [B][latent][T] (consumed),
+// output pcm [B][T * upsample].  Every op is a causal convolution: look-back 9.4 frames in total.
+void voc_back(const q3_model* m, const VocBufs& w, int B, int T, float* pcm, cudaStream_t st) {
+  const VocoderW& v = m->voc;
   int len = T;
-  float* cur = A;
-  float* o1 = Bf;
-  float* o2 = C;
-  float* o3 = D;
+  float* cur = w.A;
+  float* o1 = w.Bf;
+  float* o2 = w.C;
+  float* o3 = w.D;
   for (const VUpsample& u : v.ups) {
     launch_tconv(u.tconv, u.ratio, cur, o1, B, len, nullptr, st);
     len *= u.ratio;
@@ -414,4 +441,43 @@ void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes
     }
   }
   launch_conv(v.final_conv, cur, pcm, B, len, 1, &v.final_snake, nullptr, nullptr, CEPI_CLAMP, st);
+}
+
+}  // namespace
+
+void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes, int B, int T, float* pcm, cudaStream_t st) {
+  Q3_REQUIRE(m->has_vocoder, Q3_ERR_STATE, "vocoder weights were not loaded");
+  if (B <= 0 || T <= 0) return;
+  Q3_REQUIRE(T <= 3072, Q3_ERR_UNSUPPORTED, "vocoder: at most 3072 frames per call");
+  const VocBufs w = voc_ensure(m, ws, B, T);
+  voc_embed(m, ws, w, codes, B, T, w.A, st);
+  voc_transformer(m, ws, w, B, T, 0, nullptr, nullptr, 0, st);
+  voc_back(m, w, B, T, pcm, st);
+}
+
+void vocoder_stream_chunk(const q3_model* m, VocoderWorkspace& ws, VocoderStreamState& ss, const long long* codes_win, int B,
+                          int f0, int T, float* pcm, cudaStream_t st) {
+  Q3_REQUIRE(m->has_vocoder, Q3_ERR_STATE, "vocoder weights were not loaded");
+  if (B <= 0 || T <= 0) return;
+  const q3_model_desc& d = m->d;
+  Q3_REQUIRE(ss.cap > 0 && f0 == ss.frames && f0 + T <= ss.cap, Q3_ERR_STATE, "vocoder stream state out of step");
+  Q3_REQUIRE(f0 + T <= 3072, Q3_ERR_UNSUPPORTED, "vocoder: at most 3072 frames per utterance");
+  const int c0 = std::min(VOC_STREAM_FRONT_CTX, f0), Tw = c0 + T;
+  const int cb = std::min(VOC_STREAM_BACK_CTX, f0), Tb = cb + T;
+  const VocBufs w = voc_ensure(m, ws, B, std::max(Tw, Tb));
+  const int Hd = d.v_hidden, Lt = d.v_latent_dim;
+  // ---- front half over the new frames ----
+  // embed [f0 - c0, f0 + T): the k = 3 pre-conv sees its true left context, the c0 leading outputs are dropped
+  voc_embed(m, ws, w, codes_win, B, Tw, w.D, st);
+  Q3_CHECK_CUDA(cudaMemcpy2DAsync(w.A, (size_t)T * sizeof(float), w.D + c0, (size_t)Tw * sizeof(float), (size_t)T * sizeof(float),
+                                  (size_t)B * Hd, cudaMemcpyDeviceToDevice, st));
+  voc_transformer(m, ws, w, B, T, f0, ss.kc.as<float>(), ss.vc.as<float>(), ss.cap, st);
+  // keep the front half's output of every frame: the back half of the NEXT chunks needs the last 10 as left context
+  Q3_CHECK_CUDA(cudaMemcpy2DAsync(ss.front.as<float>() + f0, (size_t)ss.cap * sizeof(float), w.A, (size_t)T * sizeof(float),
+                                  (size_t)T * sizeof(float), (size_t)B * Lt, cudaMemcpyDeviceToDevice, st));
+  // ---- back half over [f0 - cb, f0 + T) ----
+  Q3_CHECK_CUDA(cudaMemcpy2DAsync(w.A, (size_t)Tb * sizeof(float), ss.front.as<float>() + (f0 - cb), (size_t)ss.cap * sizeof(float),
+                                  (size_t)Tb * sizeof(float), (size_t)B * Lt, cudaMemcpyDeviceToDevice, st));
+  voc_back(m, w, B, Tb, pcm, st);
+  ss.frames = f0 + T;
 }

@@ -341,19 +341,21 @@ __global__ void __launch_bounds__(256) voc_channel_norm_kernel(const float* __re
 }
 
 // ---- vocoder transformer attention ------------------------------------------------------------------------
-// RoPE (rotate-half within head_dim, decoder_12hz.rs:682-691) + relayout [B][H*D][T] -> [B][H][T][D]
+// RoPE (rotate-half within head_dim, decoder_12hz.rs:682-691) + relayout [B][H*D][T] -> [B][H][To][D] at row to0 + t.
+// pos0: absolute position of column 0 (0 for a whole utterance; the number of frames already decoded for a streamed chunk,
+// whose keys and values are appended to the session's cache: To = cache capacity, to0 = pos0).
 __global__ void voc_rope_relayout_kernel(const float* __restrict__ x, float* __restrict__ out, int H, int D, int T,
-                                         float theta, int apply_rope) {
+                                         float theta, int apply_rope, int pos0, int To, int to0) {
   const int b = blockIdx.z, h = blockIdx.y, t = blockIdx.x;
   const float* xb = x + ((size_t)b * H * D + (size_t)h * D) * T;
-  float* ob = out + (((size_t)b * H + h) * T + t) * D;
+  float* ob = out + (((size_t)b * H + h) * To + to0 + t) * D;
   const int half = D / 2;
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     float v = xb[(size_t)d * T + t];
     if (apply_rope) {
       int i = d % half;
       float inv = 1.0f / powf(theta, (float)(2 * i) / (float)D);
-      float ang = (float)t * inv;
+      float ang = (float)(pos0 + t) * inv;
       float cs = cosf(ang), sn = sinf(ang);
       float rot = d < half ? -xb[(size_t)(d + half) * T + t] : xb[(size_t)(d - half) * T + t];
       v = v * cs + rot * sn;
@@ -362,20 +364,23 @@ __global__ void voc_rope_relayout_kernel(const float* __restrict__ x, float* __r
   }
 }
 
-// causal attention, one warp per query; q,k,v: [B][H][T][D] (D <= 128); out: channel-major [B][H*D][T]
+// causal attention, one warp per query; q: [B][H][T][D] (D <= 128), k,v: [B][H][Tk][D] holding positions 0 .. pos0 + T - 1
+// (Tk = T, pos0 = 0 for a whole utterance; the session's cache for a streamed chunk); query t sits at position pos0 + t and
+// attends to positions <= pos0 + t; out: channel-major [B][H*D][T].  Shared memory: 4 x (pos0 + T) floats.
 __global__ void __launch_bounds__(128) voc_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                        const float* __restrict__ v, float* __restrict__ out, int H, int D,
-                                                       int T, float scale) {
-  extern __shared__ float sm_vattn[];             // [4 warps][T] scores
+                                                       int T, float scale, int Tk, int pos0) {
+  extern __shared__ float sm_vattn[];             // [4 warps][pos0 + T] scores
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, t = blockIdx.x * 4 + warp;
   if (t >= T) return;
-  float* sc = sm_vattn + (size_t)warp * T;
+  const int last = pos0 + t;
+  float* sc = sm_vattn + (size_t)warp * (pos0 + T);
   const float* qv = q + (((size_t)b * H + h) * T + t) * D;
-  const float* kb = k + ((size_t)b * H + h) * T * D;
-  const float* vb = v + ((size_t)b * H + h) * T * D;
+  const float* kb = k + ((size_t)b * H + h) * Tk * D;
+  const float* vb = v + ((size_t)b * H + h) * Tk * D;
   float m = -INFINITY;
-  for (int j = lane; j <= t; j += 32) {
+  for (int j = lane; j <= last; j += 32) {
     const float* kv = kb + (size_t)j * D;
     float d = 0.f;
     for (int e = 0; e < D; ++e) d = fmaf(qv[e], kv[e], d);
@@ -385,7 +390,7 @@ __global__ void __launch_bounds__(128) voc_attn_kernel(const float* __restrict__
   }
   m = warp_max(m);
   float sum = 0.f;
-  for (int j = lane; j <= t; j += 32) {
+  for (int j = lane; j <= last; j += 32) {
     float e = expf(sc[j] - m);
     sc[j] = e;
     sum += e;
@@ -395,7 +400,7 @@ __global__ void __launch_bounds__(128) voc_attn_kernel(const float* __restrict__
   const float inv = 1.0f / sum;
   for (int d0 = lane; d0 < D; d0 += 32) {
     float acc = 0.f;
-    for (int j = 0; j <= t; ++j) acc = fmaf(sc[j], vb[(size_t)j * D + d0], acc);
+    for (int j = 0; j <= last; ++j) acc = fmaf(sc[j], vb[(size_t)j * D + d0], acc);
     out[((size_t)b * H * D + (size_t)h * D + d0) * T + t] = acc * inv;
   }
 }

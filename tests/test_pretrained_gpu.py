@@ -59,6 +59,45 @@ def test_streaming_left_context_matches_non_streamed_pcm():
     assert err[0] > 1e-3 * rms and err[2] < err[0], err
 
 
+@pytest.mark.parametrize("chunk", [1, 2, 7])
+def test_stateful_streaming_equals_the_non_streamed_waveform(chunk):
+    """Stateful streaming (stream context -1): the session carries the pre-transformer's keys / values and
+    the last 10 frames of the conv stack's input, so chunks of 1, 2 or 7 frames -- 40 frames in total, i.e. up to 40 chunks,
+    most of them longer ago than the 10-frame look-back -- reproduce the non-streamed waveform of the same codes to 1e-6,
+    for a batch of two rows, and the oracle's decode of those codes within the 1e-3 RMS bar."""
+    from oracle import generate as OG, vocoder as OV
+    spec = S.SPEC_TINY
+    vw = vocoder_weights(spec.vocoder, spec.name)
+    tts = api.Qwen3TTS.from_weights(spec, talker_weights(spec), vw)
+    prompts = [W.synthetic_prompt(2, spec), W.synthetic_prompt(9, spec)]
+    F = 40
+    opts = api.SynthesisOptions(max_length=F, chunk_frames=chunk, stream_left_context=-1)
+    whole = tts.synthesize_with_voice(prompts, options=api.SynthesisOptions(max_length=F), seeds=[99, 100])
+    pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
+    sess = tts._new_session(prompts, pp, opts, [99, 100])
+    pcm = [[], []]
+    codes = [[], []]
+    n_calls = 0
+    while True:
+        c, p, n, done = sess.stream_next()
+        n_calls += 1
+        for b in range(2):
+            if n[b]:
+                pcm[b].append(p[b, : n[b] * 1920].copy())
+                codes[b] += c[b, : n[b]].tolist()
+        if done:
+            break
+    sess.close()
+    assert n_calls >= F // chunk
+    voc = OV.Vocoder(spec.vocoder, vw)
+    for b in range(2):
+        got = np.concatenate(pcm[b])
+        assert got.shape == whole[b].samples.shape
+        assert np.abs(got - whole[b].samples).max() <= 1e-6, (chunk, b, float(np.abs(got - whole[b].samples).max()))
+        ref = voc.decode(OG.codes_to_tensor(codes[b]))[0, 0].numpy()
+        assert float(np.sqrt(np.mean((got - ref) ** 2))) <= 1e-3
+
+
 def test_cuda_path_against_the_committed_golden_vectors():
     """tests/golden/tiny_model_fixture.json (frozen oracle outputs): the vocoder's PCM for the fixture codes within the
     1e-3 RMS bar, sample for sample on the frozen subsets, and the first semantic token of the fixture utterance (it
