@@ -494,6 +494,133 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
     }
     SY::sync();
   } else {
+    // ---- top-k threshold by RADIX SELECT (4 passes over an order-preserving 32-bit key), then a sort of the survivors only.
+    // Same results as the full sort below (the threshold is the exact k-th largest value, ties keep extras, and the top-p
+    // sums run over the survivors in descending order), at ~1/8 of its 78 block-wide stages.  Falls through to the full sort
+    // when top-k is off or more than 256 values tie into the survivor set.
+    bool have_thr = false;
+    if (a.top_k > 0) {
+      unsigned* hist = reinterpret_cast<unsigned*>(srt);            // [256]
+      unsigned* sel = hist + 256;                                   // [0] prefix, [1] remaining, [2] survivor count
+      float* sv = srt + 1024;                                       // [256] survivor values (sorted descending below)
+      const int k = a.top_k < V ? a.top_k : V;
+      auto okey = [](float x) -> unsigned {                          // monotone: larger float -> larger key; -inf is the smallest
+        const unsigned u = __float_as_uint(x);
+        return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      };
+      if (tid == 0) { sel[0] = 0u; sel[1] = (unsigned)k; }
+      for (int pass = 3; pass >= 0; --pass) {
+        for (int i = tid; i < 256; i += NT) hist[i] = 0u;
+        SY::sync();
+        const unsigned prefix = sel[0];
+        for (int i = tid; i < V; i += NT) {
+          const unsigned key = okey(xs[i]);
+          if (pass == 3 || (key >> (8 * (pass + 1))) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+        }
+        SY::sync();
+        if (tid < 32) {
+          // lane l owns digits 8l .. 8l+7; find the digit d with  count(digits > d) < remaining <= count(digits >= d)
+          unsigned c[8], mine = 0u;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { c[j] = hist[8 * tid + j]; mine += c[j]; }
+          unsigned above = 0u;                                       // keys in the digits of all higher lanes
+          for (int l = 31; l >= 1; --l) {
+            const unsigned v = __shfl_sync(0xffffffffu, mine, l);
+            if (l > tid) above += v;
+          }
+          const unsigned remaining = sel[1];
+          __syncwarp();
+          if (above < remaining && remaining <= above + mine) {
+            unsigned acc = above;
+            int d = 7;
+            for (; d >= 0; --d) {
+              if (remaining <= acc + c[d]) break;
+              acc += c[d];
+            }
+            sel[0] = (prefix << 8) | (unsigned)(8 * tid + d);
+            sel[1] = remaining - acc;
+          }
+        }
+        SY::sync();
+      }
+      const unsigned thr_key = sel[0];
+      if (tid == 0) sel[2] = 0u;
+      SY::sync();
+      for (int i = tid; i < V; i += NT) {
+        if (okey(xs[i]) >= thr_key) {
+          const unsigned pos = atomicAdd(&sel[2], 1u);
+          if (pos < 256u) sv[pos] = xs[i];
+        }
+      }
+      SY::sync();
+      const int n1 = (int)sel[2];
+      if (n1 <= 256) {
+        // sort the survivors descending: bitonic over the next power of two (padded with -inf); up to 64 slots (the usual
+        // case: top-k 50) one warp does it with warp barriers only
+        int npad = 2;
+        while (npad < n1) npad <<= 1;
+        for (int i = n1 + tid; i < npad; i += NT) sv[i] = -INFINITY;
+        SY::sync();
+        if (npad <= 64) {
+          if (tid < 32) {
+            for (int kk = 2; kk <= npad; kk <<= 1) {
+              for (int j = kk >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < npad; i += 32) {
+                  const int ixj = i ^ j;
+                  if (ixj > i) {
+                    const float x = sv[i], y = sv[ixj];
+                    const bool desc = ((i & kk) == 0);
+                    if (desc ? (x < y) : (x > y)) { sv[i] = y; sv[ixj] = x; }
+                  }
+                }
+                __syncwarp();
+              }
+            }
+          }
+          SY::sync();
+        } else {
+          for (int kk = 2; kk <= npad; kk <<= 1) {
+            for (int j = kk >> 1; j > 0; j >>= 1) {
+              for (int i = tid; i < npad; i += NT) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                  const float x = sv[i], y = sv[ixj];
+                  const bool desc = ((i & kk) == 0);
+                  if (desc ? (x < y) : (x > y)) { sv[i] = y; sv[ixj] = x; }
+                }
+              }
+              SY::sync();
+            }
+          }
+        }
+        if (tid == 0) {
+          float thr = sv[k - 1];                      // sampling.rs:203-211: keep >= k-th largest (ties keep extras: all n1 survivors)
+          if (a.use_top_p) {                          // sampling.rs:263-286, sums in sorted order as in the full-sort path
+            const float mx = sv[0];
+            float sum = 0.f;
+            for (int i = 0; i < n1; ++i) sum += expf(sv[i] - mx);
+            float cum = 0.f;
+            float min_kept = sv[0];
+            for (int i = 0; i < n1; ++i) {
+              if (cum >= a.top_p) break;
+              min_kept = sv[i];
+              cum += expf(sv[i] - mx) / sum;
+            }
+            thr = fmaxf(thr, min_kept);
+          }
+          s_thr = thr;
+          s_mx = sv[0];
+        }
+        have_thr = true;
+        SY::sync();
+      }
+      if (!have_thr) {
+        // restore the copy the full sort works on
+        for (int i = tid; i < 4096; i += NT) srt[i] = xs[i];
+        SY::sync();
+      }
+    }
+    if (!have_thr) {
     // bitonic sort, descending, 4096 keys / 1024 threads
     for (int k = 2; k <= 4096; k <<= 1) {
       for (int j = k >> 1; j > 0; j >>= 1) {
@@ -535,6 +662,7 @@ __device__ __forceinline__ void sample_row_body(const SampleArgs& a, const int b
       s_mx = srt[0];
     }
     SY::sync();
+    }   // full-sort path
     // compact survivors (x >= thr) in index order; one warp, ballot + popc
     if (tid < 32) {
       const float thr = s_thr, mx = s_mx;

@@ -7,6 +7,8 @@
 
 #include <cstdlib>
 
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX v3: ranges show up under nsys / ncu --nvtx, no-ops otherwise
+
 #include "decode_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
@@ -17,6 +19,14 @@
 #include "model.h"
 
 std::atomic<uint64_t> g_q3_launches{0};
+
+// Stage ranges named after the reference's tracing spans (src/lib.rs:433-485 "synthesize" / "prefill" / "decode",
+// 578 "generate_frames"): the per-frame spans of the reference (code_predictor / talker_step / sampling, lib.rs:593-637)
+// live INSIDE one persistent kernel launch here and are timed by the kernel's own stamps (tools/profile_mega2.py).
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 static thread_local std::string g_last_error;
 
 // =================================================================================================
@@ -720,6 +730,7 @@ static void run_frames_mega(q3_session* s, int n) {
 
 static void run_frames(q3_session* s, int n) {
   if (n <= 0) return;
+  NvtxRange nvtx("generate_frames");
   // KV overflow check (kv_cache.rs:293-300)
   int max_len = 0;
   for (int b = 0; b < s->B; ++b) max_len = std::max(max_len, s->prefill_len[b]);
@@ -1235,6 +1246,7 @@ q3_status q3_session_synchronize(q3_session* s) {
 
 // prefill over device-resident embeddings x [B][l_max][H] (in scratch x)
 static void prefill_run(q3_session* s, const int32_t* lens, int l_max) {
+  NvtxRange nvtx("prefill");
   const q3_model* m = s->m;
   const q3_model_desc& d = m->d;
   const int B = s->B, T = B * l_max;
@@ -1411,6 +1423,7 @@ q3_status q3_generate(q3_session* s, int32_t max_frames, uint32_t* codes, int32_
 // ones a single decode of the whole utterance produces.
 static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& row_len, float* pcm_host, size_t pcm_row_stride,
                         int left_ctx = 0) {
+  NvtxRange nvtx("decode");
   const q3_model* m = s->m;
   const int B = s->B, up = vocoder_total_upsample(m);
   if (T <= 0) return;
@@ -1444,6 +1457,7 @@ static void vocode_rows(q3_session* s, int f0, int T, const std::vector<int>& ro
 // the utterance is, and the samples equal the ones a single decode of the whole utterance produces (every op is causal; the
 // conv stack looks back 9.4 frames).  No reference counterpart: lib.rs:1755-1758 decodes chunks statelessly.
 static void vocode_rows_stateful(q3_session* s, int f0, int T, const std::vector<int>& row_len, float* pcm_host, size_t pcm_row_stride) {
+  NvtxRange nvtx("decode");
   const q3_model* m = s->m;
   const q3_model_desc& d = m->d;
   const int B = s->B, up = vocoder_total_upsample(m);
