@@ -43,7 +43,7 @@ typedef unsigned long long u64;
 
 enum M2Kind { M2_GEMV = 0, M2_ATTN = 1, M2_PROLOGUE = 2, M2_GATHER = 3, M2_FINISH = 4, M2_COPYIN = 5, M2_SAMPLE = 6 };
 enum M2Fmt { XF_BF16T = 0, XF_F32T = 1, XF_GATHER = 2, XF_NONE = 3 };
-enum M2Flags { PF_WAIT_ACQ = 1, PF_ARRIVE_REL = 2, PF_DUAL = 4, PF_NORM = 8, PF_CP = 16, PF_CP0 = 32 };
+enum M2Flags { PF_WAIT_ACQ = 1, PF_ARRIVE_REL = 2, PF_DUAL = 4, PF_NORM = 8, PF_CP = 16, PF_CP0 = 32, PF_RING = 64 };
 
 struct alignas(16) M2Phase {   // 160 bytes
   const bf16* W;        // GEMV: weights [N][K]; ATTN: K cache of the layer

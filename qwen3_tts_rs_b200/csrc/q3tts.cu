@@ -16,6 +16,7 @@
 #include "mega2.cuh"
 #include "mega3.cuh"
 #include "mega4.cuh"
+#include "mega5.cuh"
 #include "model.h"
 
 std::atomic<uint64_t> g_q3_launches{0};
@@ -73,8 +74,8 @@ struct q3_session {
   std::vector<DBuf> m2_progs;      // cached full-frame program of every row group
   std::vector<int> m2_group_nph;
   int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
-  size_t m2_smem = 0, m3_smem = 0, m4_smem = 0;
-  int m4_slots = 0, m4_red2 = 0;
+  size_t m2_smem = 0, m3_smem = 0, m4_smem = 0, m5_smem = 0;
+  int m4_slots = 0, m4_red2 = 0, m5_slots = 0;
   DBuf prof;                       // optional timestamp buffer (q3_debug_profile)
   float* tap_cp_logits = nullptr;  // q3_debug_generate_tapped: device [15][B][cp_vocab] written by every frame's CP heads
   size_t mega_smem = 0;
@@ -555,6 +556,10 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
     sp.flags = PF_WAIT_ACQ | PF_ARRIVE_REL;
     pr.push_back(sp);
   }
+  // generation 5 (mega5.cuh): the register-resident phases take their weights from the TMA ring
+  if (s->mega_ver == 5)
+    for (M2Phase& ph : pr)
+      if (m5_ring_phase(ph.kind, ph.small, ph.K) && m5_region_bytes(ph.N, ph.K, ph.flags & PF_DUAL, G) <= (size_t)s->m5_slots) ph.flags |= PF_RING;
   // L2 prefetch plan (Q3_PREFETCH: 0 none, 1 the next skinny-GEMM phase's rows at the end of every GEMV phase,
   // 2 (default) additionally: the attention phase requests the gate/up rows two phases ahead at its start and the
   // o_proj phase that follows requests nothing)
@@ -614,7 +619,7 @@ static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   a.pf_sleep = e3 ? std::atoi(e3) : 200;
   const char* e4 = std::getenv("Q3_RING_SHIFT");
   a.ring_shift = e4 ? std::min(3, std::max(0, std::atoi(e4))) : 3;
-  a.m4_slots = s->m4_slots; a.m4_red2 = s->m4_red2;
+  a.m4_slots = s->mega_ver == 5 ? s->m5_slots : s->m4_slots; a.m4_red2 = s->m4_red2;
   return a;
 }
 
@@ -639,7 +644,10 @@ static void mega2_launch(q3_session* s, M2Args& a, const DBuf& prog, int n_ph, b
     if (a.prof_mode == 2 && (size_t)a.prof_cap < (size_t)(n_ph * 4 + 8) * s->mega_grid + 2048) a.prof_mode = 0;
   }
   void* params[] = {(void*)&a};
-  if (s->mega_ver == 4 && !force_v2)
+  if (s->mega_ver == 5 && !force_v2)
+    Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega5_kernel, dim3(s->mega_grid), dim3(MEGA_THREADS), params,
+                                              s->m5_smem, s->st));
+  else if (s->mega_ver == 4 && !force_v2)
     Q3_CHECK_CUDA(cudaLaunchCooperativeKernel((const void*)decode_frames_mega4_kernel, dim3(s->mega_grid), dim3(M4_THREADS), params,
                                               s->m4_smem, s->st));
   else if (s->mega_ver == 3 && !force_v2)
@@ -1194,6 +1202,20 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
             Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, decode_frames_mega4_kernel, M4_THREADS, s->m4_smem));
           }
           if (per_sm4 >= 1) s->mega_ver = 4;
+        }
+        // generation 5 (mega5.cuh): mega2's phases with the register-resident ones fed by a TMA ring; Q3_MEGA=5
+        const bool want5 = env && env[0] == '5';
+        if (want5) {
+          size_t work5 = 0;
+          const size_t cap5 = mega5_buffer_cap(d, std::min(B, (int)MEGA_TMAX), max_seq, m->num_sms, &work5);
+          s->m5_slots = (int)cap5;                 // bytes of the prefetch buffer
+          s->m5_smem = cap5 ? cap5 + work5 : 0;
+          int per_sm5 = 0;
+          if (s->m5_smem > 0) {
+            Q3_CHECK_CUDA(cudaFuncSetAttribute(decode_frames_mega5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->m5_smem));
+            Q3_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm5, decode_frames_mega5_kernel, MEGA_THREADS, s->m5_smem));
+          }
+          if (per_sm5 >= 1) s->mega_ver = 5;
         }
 #ifdef Q3_ALL_GENERATIONS
       } else if (v1_ok) {

@@ -237,7 +237,7 @@ def test_full_size_1p7b_batch8_properties():
         assert all((f[0] < 2048) for f in row) and all(max(f[1:]) < 2048 for f in row)
 
 
-@pytest.mark.parametrize("mega", ["1", "2", "3", "4"])
+@pytest.mark.parametrize("mega", ["1", "2", "3", "4", "5"])
 def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
     """The generations of the persistent frame kernel -- fence-based grid barriers (Q3_MEGA=1), tagged dataflow phases (2),
     the round-1 TMA weight-ring variant (3) and the warp-specialised TMA ring of round 2 (4, the default where every
@@ -251,7 +251,7 @@ def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
     monkeypatch.setenv("Q3_MEGA", mega)
     # generation 4 needs every skinny-GEMM K to be a multiple of 1024: SPEC_RING has the 1.7B's matrix shapes (K = 1024, 2048,
     # 3072, 6144; 48-row gate/up tiles) with 2 + 2 layers; the others run the mid spec as in round 1
-    spec = S.SPEC_RING if mega == "4" else S.SPEC_MID
+    spec = S.SPEC_RING if mega in ("4", "5") else S.SPEC_MID
     B, F = 4, 40
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(10 + i, spec) for i in range(B)]

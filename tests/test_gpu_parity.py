@@ -134,7 +134,8 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
 
 
 @pytest.mark.parametrize("spec,mega", [(S.SPEC_TINY, None), (S.SPEC_TINY_PROJ, None), (S.SPEC_MID, None), (S.SPEC_RING, None),
-                                       (S.SPEC_RING, "4")], ids=["tiny", "tiny_proj", "mid", "ring", "ring-mega4"])
+                                       (S.SPEC_RING, "4"), (S.SPEC_RING, "5"), (S.SPEC_MID, "5")],
+                         ids=["tiny", "tiny_proj", "mid", "ring", "ring-mega4", "ring-mega5", "mid-mega5"])
 def test_free_running_generate_follows_the_oracle_every_frame(spec, mega, monkeypatch):
     """64 frames, batch 8 (4 launches of 16 frames in the production path): tapped run == untapped run bit for bit, and
     three rows are held to the oracle at every frame (module docstring, items 1-6).  "ring" has the 1.7B's matrix shapes
@@ -159,8 +160,8 @@ def test_free_running_generate_follows_the_oracle_every_frame(spec, mega, monkey
     assert rep["oracle_argmax_differs"] <= rep["codes"] // 20       # near-ties (each one verified above) stay a small minority
 
 
-@pytest.mark.parametrize("spec,batch,mega", [(S.SPEC_1_7B, 8, None), (S.SPEC_1_7B, 1, None), (S.SPEC_0_6B, 8, None), (S.SPEC_1_7B, 8, "4")],
-                         ids=["1.7b-b8", "1.7b-b1", "0.6b-b8", "1.7b-b8-mega4"])
+@pytest.mark.parametrize("spec,batch,mega", [(S.SPEC_1_7B, 8, None), (S.SPEC_1_7B, 1, None), (S.SPEC_0_6B, 8, None), (S.SPEC_1_7B, 8, "4"), (S.SPEC_1_7B, 8, "5"), (S.SPEC_0_6B, 8, "5")],
+                         ids=["1.7b-b8", "1.7b-b1", "0.6b-b8", "1.7b-b8-mega4", "1.7b-b8-mega5", "0.6b-b8-mega5"])
 def test_baseline_dimensions_follow_the_oracle(spec, batch, mega, monkeypatch):
     """BASELINE.json's model dimensions (1.7B: hidden 2048, 28 layers, 16/8 heads, inter 6144, small_to_mtp projection;
     0.6B: hidden 1024, inter 3072, no projection), batch 8 and batch 1, 3 frames: the same six checks, i.e. the K = 6144
@@ -182,7 +183,7 @@ def test_baseline_dimensions_follow_the_oracle(spec, batch, mega, monkeypatch):
     assert rep["frames"] == len(rows) * F and rep["sample_exempt"] == 0
 
 
-@pytest.mark.parametrize("mega", ["2", "4"])
+@pytest.mark.parametrize("mega", ["2", "4", "5"])
 def test_code_predictor_frame_repeats_bit_for_bit_at_1p7b(mega, monkeypatch):
     """Race detector at BASELINE dimensions: the code-predictor frame (405 dependent phases of the persistent kernel, one
     launch) run 150 times on identical inputs must give bit-identical logits every time, on both generations.  (This is the

@@ -51,6 +51,17 @@ for rep in range(3):
         n += len(chunk.samples)
     dt = time.perf_counter() - t0
 line("configs[3] 1.7B VoiceDesign, batch 1, streaming (chunk 10 frames)", n // 1920, dt, f" TTFA {first*1e3:.1f} ms")
+# the same stream, STATEFUL (carried vocoder state): 2-frame chunks, PCM identical to the non-streamed decode
+opts2 = api.SynthesisOptions(max_length=120, seed=42, chunk_frames=2, stream_left_context=-1)
+for rep in range(3):
+    t0 = time.perf_counter()
+    st = tts.synthesize_voice_design_streaming(text, instr, options=opts2)
+    first = None; n = 0
+    for chunk in st:
+        if first is None: first = time.perf_counter() - t0
+        n += len(chunk.samples)
+    dt = time.perf_counter() - t0
+line("configs[3] stateful streaming, chunk 2 frames (exact PCM)", n // 1920, dt, f" TTFA {first*1e3:.1f} ms")
 for b in (4, 32):
     nf, dt = run_batch(tts, prompts[:b], 128)
     line(f"configs[4] 1.7B CustomVoice, {b} utterances on this GPU (8-GPU share = 4)", nf, dt)
