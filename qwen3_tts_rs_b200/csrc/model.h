@@ -85,6 +85,7 @@ struct VConv {
   const float* b = nullptr;
   int cin = 0, cout = 0, k = 1;
   const bf16 *w_hi = nullptr, *w_lo = nullptr;   // tensor-core layout: bf16 hi/lo split, [k][chunks][Cout_pad][32]
+  const bf16* w_um = nullptr;                    // tcgen05 layout (vocoder_umma.cuh): 16 KB shared-memory image per (tap, chunk, 128 rows)
   int cout_pad = 0, chunks = 0;
 };
 struct VSnake { const float* ea = nullptr; const float* ib = nullptr; };

@@ -8,6 +8,7 @@
 #include "model.h"
 #include "vocoder_kernels.cuh"
 #include "vocoder_mma.cuh"
+#include "vocoder_umma.cuh"
 
 namespace {
 
@@ -67,6 +68,18 @@ VConv make_conv(q3_model* m, const std::string& wname, const std::string& bname,
   c.w_lo = lo.as<bf16>();
   m->owned.push_back(std::move(hi));
   m->owned.push_back(std::move(lo));
+  if (c.cin % MC_BK == 0) {
+    // tcgen05 layout: the shared-memory image of every (tap, chunk, 128-row tile)
+    const size_t nu = (size_t)c.k * c.chunks * (c.cout_pad / MC_BM) * UC_A_ELEMS;
+    DBuf um;
+    um.alloc(nu * sizeof(bf16));
+    voc_pack_umma_weights_kernel<<<512, 256>>>(w.buf.as<float>(), um.as<bf16>(), c.cout, c.cin, c.k, c.cout_pad, c.chunks,
+                                               transposed ? 1 : 0);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    c.w_um = um.as<bf16>();
+    m->owned.push_back(std::move(um));
+  }
   return c;
 }
 
@@ -95,7 +108,38 @@ bool use_mma_path() {
   return v == 1;
 }
 
-void launch_mma(MmaConvArgs& a, int grid_q, int Cout_pad, int z, cudaStream_t st) {
+// Which convolutions run on the tcgen05 kernel: Q3_VOC_UMMA = bit mask (1: 1x1, 2: k > 1 undilated, 4: dilated, 8: transposed
+// phases); default all, 0 = the mma.sync kernel everywhere (A/B runs, tools/voc_ab.py).
+int umma_mask() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("Q3_VOC_UMMA");
+    v = e ? std::atoi(e) : 15;
+  }
+  return v;
+}
+
+void launch_mma(MmaConvArgs& a, int grid_q, int Cout_pad, int z, cudaStream_t st, int kind_bit) {
+  const int halo = a.max_shift - a.min_shift;
+  if ((umma_mask() & kind_bit) && a.w_um != nullptr && a.Cin % MC_BK == 0 && MC_BN + halo <= UC_MAX_BROWS) {
+    const size_t smem_u = umma_conv_smem_bytes(halo);
+    {
+      static std::mutex mu;
+      static bool configured[64] = {};
+      int dev = 0;
+      Q3_CHECK_CUDA(cudaGetDevice(&dev));
+      std::lock_guard<std::mutex> lock(mu);
+      if (dev < 0 || dev >= 64 || !configured[dev]) {
+        Q3_CHECK_CUDA(cudaFuncSetAttribute(voc_conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)umma_conv_smem_bytes(UC_MAX_BROWS - MC_BN)));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+      }
+    }
+    voc_conv_umma_kernel<<<dim3(grid_q, Cout_pad / MC_BM, z), UC_THREADS, smem_u, st>>>(a);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    return;
+  }
   const size_t smem = mma_conv_smem_bytes(a.max_shift - a.min_shift);
   {
     // per-DEVICE function attribute (see gemm_tc_launch)
@@ -121,7 +165,7 @@ void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil
                  const float* scale, int epi, cudaStream_t st) {
   if (use_mma_path() && c.cout >= 16 && c.k <= MC_MAX_TAPS) {
     MmaConvArgs m{};
-    m.x = x; m.w_hi = c.w_hi; m.w_lo = c.w_lo; m.bias = c.b;
+    m.x = x; m.w_hi = c.w_hi; m.w_lo = c.w_lo; m.w_um = c.w_um; m.bias = c.b;
     m.snake_a = snake ? snake->ea : nullptr; m.snake_ib = snake ? snake->ib : nullptr;
     m.res = res; m.scale = scale; m.y = y;
     m.B = B; m.Cin = c.cin; m.Cout = c.cout; m.Cout_pad = c.cout_pad; m.Tin = T; m.Tout = T; m.Q = T;
@@ -129,7 +173,7 @@ void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil
     for (int j = 0; j < c.k; ++j) { m.tap_w[j] = j; m.tap_shift[j] = -(c.k - 1 - j) * dil; }
     m.min_shift = -(c.k - 1) * dil; m.max_shift = 0;
     m.out_stride = 1; m.out_off = 0; m.epi = epi; m.phases = 1; m.phase_tap_step = 0;
-    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B, st);
+    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B, st, c.k == 1 ? 1 : (dil == 1 ? 2 : 4));
     return;
   }
   if (c.cout == 1 && dil == 1 && res == nullptr && scale == nullptr && (epi == CEPI_NONE || epi == CEPI_CLAMP)) {
@@ -160,7 +204,7 @@ void launch_tconv(const VConv& c, int stride, const float* x, float* y, int B, i
   if (use_mma_path() && c.cout >= 16 && (c.k == stride || c.k == 2 * stride)) {
     // phase r in [0, stride): y[co][stride*q + r] = b + sum_ci x[ci][q] w[ci][co][r] (+ x[ci][q-1] w[ci][co][r+stride])
     MmaConvArgs m{};
-    m.x = x; m.w_hi = c.w_hi; m.w_lo = c.w_lo; m.bias = c.b;
+    m.x = x; m.w_hi = c.w_hi; m.w_lo = c.w_lo; m.w_um = c.w_um; m.bias = c.b;
     m.snake_a = snake ? snake->ea : nullptr; m.snake_ib = snake ? snake->ib : nullptr;
     m.y = y; m.B = B; m.Cin = c.cin; m.Cout = c.cout; m.Cout_pad = c.cout_pad; m.Tin = T; m.Tout = T * stride; m.Q = T;
     if (c.k == 2 * stride) {
@@ -174,7 +218,7 @@ void launch_tconv(const VConv& c, int stride, const float* x, float* y, int B, i
       m.min_shift = 0;
     }
     m.max_shift = 0; m.out_stride = stride; m.out_off = 0; m.epi = CEPI_NONE; m.phases = stride; m.phase_tap_step = 1;
-    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B * stride, st);
+    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B * stride, st, 8);
     return;
   }
   TConvArgs a;

@@ -26,6 +26,7 @@ struct MmaConvArgs {
   const float* x;         // [B][Cin][Tin]
   const bf16* w_hi;       // packed [ntaps_total][chunks][Cout_pad][32]  (Cout_pad = multiple of 128)
   const bf16* w_lo;
+  const bf16* w_um;       // the same weights as shared-memory images of the tcgen05 kernel (vocoder_umma.cuh), or null
   const float* bias;      // [Cout] or null
   const float* snake_a;   // [Cin] or null
   const float* snake_ib;
