@@ -351,7 +351,7 @@ def main():
     # ---- headline: weak scaling, B utterances per GPU ------------------------------------------------
     leg = Leg(tts, spec, lib, B, F, rank * B, local_rank)
     kernel = {0: "multi-kernel CUDA graph (gemv_kernel ...)", 1: "decode_frames_mega_kernel", 2: "decode_frames_mega2_kernel",
-              3: "decode_frames_mega3_kernel", 4: "decode_frames_mega4_kernel"}[leg.sess.decode_generation()]
+              3: "decode_frames_mega3_kernel", 4: "decode_frames_mega4_kernel", 5: "decode_frames_mega5_kernel"}[leg.sess.decode_generation()]
     m = measure(leg, args.steps, warm, rank, world, B * world, want_clocks=True, local_rank=local_rank)
     lmax = leg.lmax
     leg.close()

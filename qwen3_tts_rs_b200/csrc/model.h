@@ -87,6 +87,7 @@ struct VConv {
   const bf16 *w_hi = nullptr, *w_lo = nullptr;   // tensor-core layout: bf16 hi/lo split, [k][chunks][Cout_pad][32]
   const bf16* w_um = nullptr;                    // tcgen05 layout (vocoder_umma.cuh): 16 KB shared-memory image per (tap, chunk, 128 rows)
   int cout_pad = 0, chunks = 0;
+  int um_rows_pad = 0;            // rows of the tcgen05 image (cout_pad; cout * stride padded for a transposed conv)
 };
 struct VSnake { const float* ea = nullptr; const float* ib = nullptr; };
 struct VLayer { const float *in_ln, *post_ln, *attn_scale, *mlp_scale; VConv q, k, v, o, gate, up, down; };

@@ -34,7 +34,7 @@ __global__ void repack_conv_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
-VConv make_conv(q3_model* m, const std::string& wname, const std::string& bname, bool transposed) {
+VConv make_conv(q3_model* m, const std::string& wname, const std::string& bname, bool transposed, int tconv_stride = 0) {
   const RawTensor& w = need(m, wname);
   VConv c;
   if (w.shape.size() == 2) {               // Linear [out][in] == 1x1 conv
@@ -69,12 +69,17 @@ VConv make_conv(q3_model* m, const std::string& wname, const std::string& bname,
   m->owned.push_back(std::move(hi));
   m->owned.push_back(std::move(lo));
   if (c.cin % MC_BK == 0) {
-    // tcgen05 layout: the shared-memory image of every (tap, chunk, 128-row tile)
-    const size_t nu = (size_t)c.k * c.chunks * (c.cout_pad / MC_BM) * UC_A_ELEMS;
+    // tcgen05 layout: the shared-memory image of every (tap, chunk, 128-row tile).  A transposed conv of stride s is packed
+    // as ONE GEMM whose rows are (output channel, phase r < s) pairs, row = co * s + r, with k / s taps (launch_tconv)
+    const int s = transposed ? tconv_stride : 1;
+    const bool tc = transposed && s > 0 && (c.k == s || c.k == 2 * s);
+    c.um_rows_pad = tc ? ceil_div(c.cout * s, MC_BM) * MC_BM : c.cout_pad;
+    const int ntp = tc ? c.k / s : c.k;
+    const size_t nu = (size_t)ntp * c.chunks * (c.um_rows_pad / MC_BM) * UC_A_ELEMS;
     DBuf um;
     um.alloc(nu * sizeof(bf16));
-    voc_pack_umma_weights_kernel<<<512, 256>>>(w.buf.as<float>(), um.as<bf16>(), c.cout, c.cin, c.k, c.cout_pad, c.chunks,
-                                               transposed ? 1 : 0);
+    voc_pack_umma_weights_kernel<<<512, 256>>>(w.buf.as<float>(), um.as<bf16>(), c.cout, c.cin, c.k, c.um_rows_pad, c.chunks,
+                                               transposed ? 1 : 0, tc ? s : 1, ntp);
     Q3_COUNT_LAUNCH();
     Q3_LAUNCH_CHECK();
     c.w_um = um.as<bf16>();
@@ -201,6 +206,22 @@ void launch_conv(const VConv& c, const float* x, float* y, int B, int T, int dil
 
 void launch_tconv(const VConv& c, int stride, const float* x, float* y, int B, int T, const VSnake* snake, cudaStream_t st) {
   Q3_REQUIRE(c.k <= 2 * stride && c.k >= stride, Q3_ERR_UNSUPPORTED, "transposed conv needs stride <= k <= 2*stride");
+  if (use_mma_path() && c.cout >= 16 && (c.k == stride || c.k == 2 * stride) && (umma_mask() & 8) && c.w_um != nullptr &&
+      c.um_rows_pad == ceil_div(c.cout * stride, MC_BM) * MC_BM) {
+    // tcgen05 kernel: ONE GEMM whose rows are (output channel, phase) pairs (voc_pack_umma_weights_kernel), so a CTA owns
+    // all `stride` phases of its channels and writes whole runs of consecutive samples (the phase-per-CTA form below writes
+    // every stride-th float of a sector from a different CTA: 6.0 ms for the last block's 192 -> 96 x3 upsample, ncu)
+    MmaConvArgs m{};
+    m.x = x; m.w_um = c.w_um; m.bias = c.b;
+    m.snake_a = snake ? snake->ea : nullptr; m.snake_ib = snake ? snake->ib : nullptr;
+    m.y = y; m.B = B; m.Cin = c.cin; m.Cout = c.cout; m.Cout_pad = c.um_rows_pad; m.Tin = T; m.Tout = T * stride; m.Q = T;
+    m.ntaps = c.k / stride;
+    for (int j = 0; j < m.ntaps; ++j) { m.tap_w[j] = j; m.tap_shift[j] = j - (m.ntaps - 1); }
+    m.min_shift = -(m.ntaps - 1); m.max_shift = 0;
+    m.out_stride = stride; m.out_off = 0; m.epi = CEPI_NONE; m.phases = 1; m.phase_tap_step = 0; m.rdiv = stride;
+    launch_mma(m, ceil_div(T, MC_BN), c.um_rows_pad, B, st, 8);
+    return;
+  }
   if (use_mma_path() && c.cout >= 16 && (c.k == stride || c.k == 2 * stride)) {
     // phase r in [0, stride): y[co][stride*q + r] = b + sum_ci x[ci][q] w[ci][co][r] (+ x[ci][q-1] w[ci][co][r+stride])
     MmaConvArgs m{};
@@ -218,7 +239,7 @@ void launch_tconv(const VConv& c, int stride, const float* x, float* y, int B, i
       m.min_shift = 0;
     }
     m.max_shift = 0; m.out_stride = stride; m.out_off = 0; m.epi = CEPI_NONE; m.phases = stride; m.phase_tap_step = 1;
-    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B * stride, st, 8);
+    launch_mma(m, ceil_div(T, MC_BN), c.cout_pad, B * stride, st, 0);
     return;
   }
   TConvArgs a;
@@ -311,7 +332,7 @@ void vocoder_finalize(q3_model* m) {
     const std::string p = "decoder.upsample." + std::to_string(s);
     VUpsample u;
     u.ratio = d.v_upsampling[s];
-    u.tconv = make_conv(m, p + ".0.conv.weight", p + ".0.conv.bias", true);
+    u.tconv = make_conv(m, p + ".0.conv.weight", p + ".0.conv.bias", true, u.ratio);
     u.cn.dw_w = needp(m, p + ".1.dwconv.conv.weight");
     u.cn.dw_b = needp(m, p + ".1.dwconv.conv.bias");
     u.cn.ln_w = needp(m, p + ".1.norm.weight");
@@ -329,7 +350,7 @@ void vocoder_finalize(q3_model* m) {
     VBlock blk;
     blk.rate = d.v_rates[b];
     blk.s = make_snake(m, bp + ".0");
-    blk.up = make_conv(m, bp + ".1.conv.weight", bp + ".1.conv.bias", true);
+    blk.up = make_conv(m, bp + ".1.conv.weight", bp + ".1.conv.bias", true, blk.rate);
     const int dils[3] = {1, 3, 9};
     for (int u = 0; u < 3; ++u) {
       const std::string up = bp + "." + std::to_string(u + 2);
@@ -413,7 +434,8 @@ void voc_transformer(const q3_model* m, VocoderWorkspace& ws, const VocBufs& w, 
   float *A = w.A, *Bf = w.Bf, *C = w.C, *D = w.D;
   const float scale = 1.0f / sqrtf((float)d.v_head_dim);
   const int Ltot = pos0 + T;
-  Q3_REQUIRE((size_t)4 * Ltot * sizeof(float) <= 48 * 1024, Q3_ERR_UNSUPPORTED, "vocoder attention: more than 3072 frames");
+  Q3_REQUIRE(voc_attn_smem_floats(Ltot, d.v_head_dim) * sizeof(float) <= 48 * 1024, Q3_ERR_UNSUPPORTED,
+             "vocoder attention: more than ~2400 frames in one utterance");
   const size_t layer_stride = (size_t)B * d.v_heads * cap * d.v_head_dim;
   int li = 0;
   for (const VLayer& L : v.layers) {
@@ -431,7 +453,7 @@ void voc_transformer(const q3_model* m, VocoderWorkspace& ws, const VocBufs& w, 
     launch_conv(L.v, Bf, C, B, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
     voc_rope_relayout_kernel<<<dim3(T, d.v_heads, B), 64, 0, st>>>(C, vdst, d.v_heads, d.v_head_dim, T, d.v_rope_theta, 0, pos0, Tk, to0);
     Q3_COUNT_LAUNCH();
-    voc_attn_kernel<<<dim3(ceil_div(T, 4), d.v_heads, B), 128, (size_t)4 * Ltot * sizeof(float), st>>>(
+    voc_attn_kernel<<<dim3(ceil_div(T, 4), d.v_heads, B), 128, voc_attn_smem_floats(Ltot, d.v_head_dim) * sizeof(float), st>>>(
         ws.qh.as<float>(), kdst, vdst, C, d.v_heads, d.v_head_dim, T, scale, Tk, pos0);
     Q3_COUNT_LAUNCH();
     Q3_LAUNCH_CHECK();

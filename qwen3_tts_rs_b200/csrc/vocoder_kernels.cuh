@@ -366,28 +366,48 @@ __global__ void voc_rope_relayout_kernel(const float* __restrict__ x, float* __r
 
 // causal attention, one warp per query; q: [B][H][T][D] (D <= 128), k,v: [B][H][Tk][D] holding positions 0 .. pos0 + T - 1
 // (Tk = T, pos0 = 0 for a whole utterance; the session's cache for a streamed chunk); query t sits at position pos0 + t and
-// attends to positions <= pos0 + t; out: channel-major [B][H*D][T].  Shared memory: 4 x (pos0 + T) floats.
+// attends to positions <= pos0 + t; out: channel-major [B][H*D][T].  The four queries of a block share every 32-key tile of K
+// through shared memory (coalesced loads; a lane then owns one key row, padded against bank conflicts); per (query, key)
+// the arithmetic and its order do not depend on how the utterance is cut into chunks, so a streamed chunk reproduces the
+// whole-utterance result bit for bit.  Shared memory: voc_attn_smem_floats(pos0 + T, D) floats.
+__host__ __device__ inline size_t voc_attn_smem_floats(int L, int D) { return (size_t)4 * L + (size_t)32 * (D + 1) + (size_t)4 * D; }
 __global__ void __launch_bounds__(128) voc_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                                        const float* __restrict__ v, float* __restrict__ out, int H, int D,
                                                        int T, float scale, int Tk, int pos0) {
-  extern __shared__ float sm_vattn[];             // [4 warps][pos0 + T] scores
+  extern __shared__ float sm_vattn[];             // [4 warps][pos0 + T] scores | K tile [32][D + 1] | q [4][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, t = blockIdx.x * 4 + warp;
-  if (t >= T) return;
-  const int last = pos0 + t;
+  const bool active = t < T;
+  const int last = pos0 + (active ? t : 0);
+  const int block_last = pos0 + min(T - 1, (int)blockIdx.x * 4 + 3);
   float* sc = sm_vattn + (size_t)warp * (pos0 + T);
-  const float* qv = q + (((size_t)b * H + h) * T + t) * D;
+  float* Ks = sm_vattn + (size_t)4 * (pos0 + T);
+  float* qs = Ks + 32 * (D + 1) + warp * D;
   const float* kb = k + ((size_t)b * H + h) * Tk * D;
   const float* vb = v + ((size_t)b * H + h) * Tk * D;
-  float m = -INFINITY;
-  for (int j = lane; j <= last; j += 32) {
-    const float* kv = kb + (size_t)j * D;
-    float d = 0.f;
-    for (int e = 0; e < D; ++e) d = fmaf(qv[e], kv[e], d);
-    d *= scale;                                   // scale applied after QK^T (decoder_12hz.rs:636-641)
-    sc[j] = d;
-    m = fmaxf(m, d);
+  if (active) {
+    const float* qv = q + (((size_t)b * H + h) * T + t) * D;
+    for (int e = lane; e < D; e += 32) qs[e] = qv[e];
   }
+  float m = -INFINITY;
+  for (int j0 = 0; j0 <= block_last; j0 += 32) {
+    __syncthreads();                              // the previous tile has been consumed (first pass: q is in place)
+    for (int i = threadIdx.x; i < 32 * D; i += 128) {
+      const int r = i / D, e = i - r * D;
+      Ks[r * (D + 1) + e] = (j0 + r <= block_last) ? kb[(size_t)(j0 + r) * D + e] : 0.f;
+    }
+    __syncthreads();
+    const int j = j0 + lane;
+    if (active && j <= last) {
+      const float* kr = Ks + lane * (D + 1);
+      float d = 0.f;
+      for (int e = 0; e < D; ++e) d = fmaf(qs[e], kr[e], d);
+      d *= scale;                                 // scale applied after QK^T (decoder_12hz.rs:636-641)
+      sc[j] = d;
+      m = fmaxf(m, d);
+    }
+  }
+  if (!active) return;
   m = warp_max(m);
   float sum = 0.f;
   for (int j = lane; j <= last; j += 32) {

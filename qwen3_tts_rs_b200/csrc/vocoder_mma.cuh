@@ -42,6 +42,7 @@ struct MmaConvArgs {
   int epi;
   int phases;                  // transposed conv: gridDim.z = B * phases, phase r adds r to tap_w / out_off
   int phase_tap_step;          // weight tap index += r * phase_tap_step (=1 for tconv)
+  int rdiv;                    // tcgen05 kernel only: GEMM row = co * rdiv + phase (transposed conv as one GEMM), 0 / 1 = plain
 };
 
 __device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const void* smem_ptr) {

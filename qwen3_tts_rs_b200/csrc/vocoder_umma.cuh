@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(UC_THREADS, 2) voc_conv_umma_kernel(const MmaC
     // ===== weight ring producer =====
     if (lane == 0) {
       const size_t tile_stride = UC_A_ELEMS;
-      const int ntile = a.Cout_pad / MC_BM;
+      const int ntile = gridDim.y;
       for (int s = 0; s < total_steps; ++s) {
         const int stage = s % UC_STAGES, it = s / UC_STAGES;
         uc_mbar_wait(a_empty + 8 * stage, (uint32_t)((it & 1) ^ 1));
@@ -221,11 +221,13 @@ __global__ void __launch_bounds__(UC_THREADS, 2) voc_conv_umma_kernel(const MmaC
     uc_mbar_wait(acc_full, 0u);
     uc_fence_after();
     const int lq = warp & 3, chalf = warp >> 2;
-    const int co = co0 + lq * 32 + lane;
+    const int mrow = co0 + lq * 32 + lane;                 // row of the GEMM: output channel, or (channel, phase) = (mrow / rdiv, mrow % rdiv)
+    const int rdiv = a.rdiv > 1 ? a.rdiv : 1;
+    const int co = mrow / rdiv;
     const bool co_ok = co < a.Cout;
     const float bv = (co_ok && a.bias) ? a.bias[co] : 0.f;
     const float sc = (co_ok && a.scale) ? a.scale[co] : 1.f;
-    const int oo = a.out_off + phase;
+    const int oo = a.out_off + phase + (mrow - co * rdiv);
     const bool vec = a.out_stride == 1 && (a.Tout & 3) == 0 && oo == 0;
 #pragma unroll 1
     for (int h = 0; h < 2; ++h) {
@@ -284,12 +286,14 @@ __global__ void __launch_bounds__(UC_THREADS, 2) voc_conv_umma_kernel(const MmaC
 
 static size_t umma_conv_smem_bytes(int halo) { return (size_t)UC_STAGES * UC_A_BYTES + (size_t)2 * 8 * (MC_BN + halo) * 16; }
 
-// weights [Cout][Cin][k] (conv) or [Cin][Cout][k] (transposed) -> for every (tap, chunk, 128-row tile) the 16 KB shared-memory
-// image: [hi | lo][k-group 0..3][row 0..127][8 bf16]
+// weights [Cout][Cin][k] (conv) or [Cin][Cout][k] (transposed) -> for every (tap slot, chunk, 128-row tile) the 16 KB
+// shared-memory image: [hi | lo][k-group 0..3][row 0..127][8 bf16].  rdiv = 1: row = output channel, tap slot = tap.
+// rdiv = s > 1 (transposed conv of stride s, k = ntp * s): row = co * s + r, and tap slot j (input shift j - (ntp - 1)) holds
+// weight tap r + (ntp - 1 - j) * s -- y[co][s q + r] = sum_ci x[ci][q] w[ci][co][r] + x[ci][q - 1] w[ci][co][r + s].
 __global__ void voc_pack_umma_weights_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int k,
-                                             int Cout_pad, int chunks, int transposed) {
-  const int ntile = Cout_pad / MC_BM;
-  const size_t n = (size_t)k * chunks * ntile * (UC_A_ELEMS / 2);      // one thread per (hi, lo) element pair
+                                             int rows_pad, int chunks, int transposed, int rdiv, int ntp) {
+  const int ntile = rows_pad / MC_BM;
+  const size_t n = (size_t)ntp * chunks * ntile * (UC_A_ELEMS / 2);      // one thread per (hi, lo) element pair
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int e = (int)(i & 7);
     size_t r = i >> 3;
@@ -300,9 +304,11 @@ __global__ void voc_pack_umma_weights_kernel(const float* __restrict__ w, bf16* 
     const int tile = (int)(r % ntile);
     r /= ntile;
     const int chunk = (int)(r % chunks), j = (int)(r / chunks);
-    const int co = tile * MC_BM + row, ci = chunk * MC_BK + kc * 8 + e;
+    const int mrow = tile * MC_BM + row, ci = chunk * MC_BK + kc * 8 + e;
+    const int co = mrow / rdiv, ph = mrow - co * rdiv;
+    const int wt = rdiv == 1 ? j : ph + (ntp - 1 - j) * rdiv;
     float v = 0.f;
-    if (co < Cout && ci < Cin) v = transposed ? w[((size_t)ci * Cout + co) * k + j] : w[((size_t)co * Cin + ci) * k + j];
+    if (co < Cout && ci < Cin && wt < k) v = transposed ? w[((size_t)ci * Cout + co) * k + wt] : w[((size_t)co * Cin + ci) * k + wt];
     const bf16 h = f2bf(v);
     const size_t base = (((size_t)j * chunks + chunk) * ntile + tile) * UC_A_ELEMS + ((size_t)kc * MC_BM + row) * 8 + e;
     out[base] = h;

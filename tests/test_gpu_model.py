@@ -240,8 +240,8 @@ def test_full_size_1p7b_batch8_properties():
 @pytest.mark.parametrize("mega", ["1", "2", "3", "4", "5"])
 def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
     """The generations of the persistent frame kernel -- fence-based grid barriers (Q3_MEGA=1), tagged dataflow phases (2),
-    the round-1 TMA weight-ring variant (3) and the warp-specialised TMA ring of round 2 (4, the default where every
-    skinny-GEMM K is a multiple of 1024) -- are all held to the same bar on a model whose
+    the round-1 TMA weight-ring variant (3), the warp-specialised TMA ring of round 2 (4) and the dataflow kernel with a TMA
+    prefetch buffer (5) -- are all held to the same bar on a model whose
     dimensions exercise the register-resident, streaming and ring code paths (hidden 2048 / CP hidden 1024):
     free-running forks from the oracle only at near-ties, identical results on a second run, and across the
     16-frame launch boundary (40 frames = 3 launches, so the session's tag counter is carried between launches)."""
@@ -249,9 +249,10 @@ def test_persistent_kernel_generations_agree_with_the_oracle(monkeypatch, mega):
     if mega in ("1", "3") and not L.IS_DEV:
         pytest.skip("historical generation: only in libq3tts_b200_dev.so (run with Q3TTS_LIB=dev)")
     monkeypatch.setenv("Q3_MEGA", mega)
-    # generation 4 needs every skinny-GEMM K to be a multiple of 1024: SPEC_RING has the 1.7B's matrix shapes (K = 1024, 2048,
-    # 3072, 6144; 48-row gate/up tiles) with 2 + 2 layers; the others run the mid spec as in round 1
-    spec = S.SPEC_RING if mega in ("4", "5") else S.SPEC_MID
+    # the ring generations (3, 4, 5) need every skinny-GEMM K to be a multiple of 1024: SPEC_RING has the 1.7B's matrix shapes
+    # (K = 1024, 2048, 3072, 6144; 48-row gate/up tiles) with 2 + 2 layers; generations 1 and 2 run the mid spec as in round 1
+    # (on which round 1's generation-3 run silently fell back to generation 2 -- hence the decode_generation() assertion)
+    spec = S.SPEC_RING if mega in ("3", "4", "5") else S.SPEC_MID
     B, F = 4, 40
     opts = api.SynthesisOptions(max_length=F)
     prompts = [W.synthetic_prompt(10 + i, spec) for i in range(B)]
