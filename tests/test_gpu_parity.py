@@ -56,9 +56,12 @@ def close_to_f32(cuda, bf, f32, what, stats):
                                       f"rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})")
 
 
-def run_tapped(tts, prompts, seeds, opts, frames):
-    pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
-    sess = tts._new_session(prompts, pp, opts, seeds)
+def run_tapped(tts, prompts, seeds, opts, frames, instruct=None):
+    if instruct is None:
+        pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
+    else:       # VoiceDesign prefill (talker.rs:585-627): the instruct ids sit in front of the role prefix
+        pp = [tts.voice_design_prompt(t, ins, "english") for t, ins in zip(prompts, instruct)]
+    sess = tts._new_session(prompts, pp, opts, seeds, max_seq=max(len(p[0]) for p in pp) + frames + 40)
     try:
         text = sess.trailing_rows(cap=max(len(t) for t in prompts) + 1)
         codes, n, taps = sess.generate_tapped(frames)
@@ -68,11 +71,11 @@ def run_tapped(tts, prompts, seeds, opts, frames):
     return [codes[b, : n[b]].tolist() for b in range(len(prompts))], taps
 
 
-def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, taps=None, models=None, models32=None):
+def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, taps=None, models=None, models32=None, instruct=None):
     """Runs the tapped CUDA loop (unless given) and holds rows `rows` to the oracle as the module docstring says.
     Returns a report dict (counts only; every violation asserts)."""
     if tapped is None:
-        tapped, taps = run_tapped(tts, prompts, seeds, opts, frames)
+        tapped, taps = run_tapped(tts, prompts, seeds, opts, frames, instruct)
     tk, cp = models if models is not None else oracle_models(spec)
     tk32, cp32 = models32 if models32 is not None else oracle_models(spec, bf16=False)
     cfg = oracle_cfg(opts)
@@ -80,18 +83,23 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
     for b in rows:
         got = tapped[b]
         n = len(got)
-        emb = tk.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+        def prefill_embeds(t):
+            if instruct is None:
+                return t.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
+            return t.voice_design_embeds(prompts[b], instruct[b], S.LANGUAGE_IDS["english"])
+        emb = prefill_embeds(tk)
+        kv_max = int(emb.shape[1]) + frames + 64
         tr_rows, tr_lt, tr_pad = taps["text"]
         gpu_text = (tr_rows[b, : int(tr_lt[b])][None], tr_pad[None, None])
         fo = OG.follow(tk, cp, emb, prompts[b], cfg, seeds[b], got, first_logits=taps["first_logits"][b],
-                       frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=frames + 64, text_rows=gpu_text)
+                       frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=kv_max, text_rows=gpu_text)
         # the device's text projection (trailing rows + tts_pad) vs the oracle's: the same noise-calibrated bar as the logits
         o_tr = torch.cat([fo["text"]["trailing"][0], fo["text"]["pad"][0]], 0)
         g_tr = torch.cat([gpu_text[0][0].float(), gpu_text[1][0].float()], 0)
         f_tr32, f_len, f_pad32 = tk32.build_trailing_text(prompts[b])
         close_to_f32(g_tr, o_tr, torch.cat([f_tr32[0], f_pad32[0]], 0), f"trailing text rows row {b}", rep)
-        emb32 = tk32.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
-        f32 = OG.follow(tk32, cp32, emb32, prompts[b], cfg, seeds[b], got, kv_max=frames + 64)      # noise calibration (item 5)
+        emb32 = prefill_embeds(tk32)
+        f32 = OG.follow(tk32, cp32, emb32, prompts[b], cfg, seeds[b], got, kv_max=kv_max)      # noise calibration (item 5)
         # 1. RNG stream
         assert [int(x) for x in taps["rng"][: n + 1, b]] == fo["rng_states"], ("rng stream", b)
         # 2. sampler replay on the CUDA path's own logits
@@ -228,3 +236,22 @@ def test_eos_row_follows_the_oracle_to_its_last_frame():
     models32 = (OM.Talker(spec, w, OM.F32P), OM.CodePredictor(spec, w, OM.F32P))
     rep = check_follow(spec, tts, prompts, seeds, opts, 12, rows=(0, 1), tapped=tapped, taps=taps, models=models, models32=models32)
     assert rep["sampled"] == 2 * 3 and rep["sample_exempt"] == 0      # first token, token after frame 0, EOS after frame 1
+
+
+def test_long_context_voice_design_prefill_follows_the_oracle():
+    """Long context at BASELINE dimensions (0.6B: 28 layers, 16 query / 8 kv heads): a VoiceDesign prompt whose 700 instruct
+    ids sit in the prefill (talker.rs:585-627: context = 700 + 9 positions before the first frame), batch 2 with one short
+    row, then 3 decode frames -- the prefill attention, the decode attention over ~710 cached positions of 8 kv heads and the
+    RoPE table far from position 0 are held to the oracle by the same six checks."""
+    spec = S.SPEC_0_6B
+    F = 3
+    opts = api.SynthesisOptions(max_length=F)
+    prompts = [W.synthetic_prompt(i, spec) for i in range(2)]
+    g = torch.Generator().manual_seed(99)
+    instruct = [torch.randint(0, 150000, (700,), generator=g).tolist(), torch.randint(0, 150000, (5,), generator=g).tolist()]
+    seeds = [7, 8]
+    tts = gpu_tts(spec)
+    tapped, taps = run_tapped(tts, prompts, seeds, opts, F, instruct)
+    rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=(0, 1), tapped=tapped, taps=taps, instruct=instruct)
+    print("follow report:", rep)
+    assert rep["frames"] == 2 * F and rep["sample_exempt"] == 0
