@@ -105,7 +105,8 @@ struct SynthesisOptions {
   int32_t chunk_frames = 10;
   int32_t min_new_tokens = 2;
   std::optional<uint64_t> seed;
-  /* not in the reference (opt-in, see q3_session_set_stream_context): left-context frames per streamed chunk, -1 = all */
+  /* not in the reference (opt-in, see q3_session_set_stream_context): 0 = the reference's stateless chunks, < 0 = stateful
+     streaming (carried vocoder state, streamed PCM == non-streamed PCM), c > 0 = c left-context frames decoded again */
   int32_t stream_left_context = 0;
 
   q3_gen_config to_gen_config() const {

@@ -46,8 +46,9 @@ class SynthesisOptions:
     chunk_frames: int = 10
     min_new_tokens: int = 2
     seed: Optional[int] = None
-    # Not in the reference (opt-in): frames of left context decoded again in front of every streamed
-    # chunk and dropped; -1 = the whole history (streamed PCM == non-streamed PCM), 0 = the reference's stateless chunks.
+    # Not in the reference (opt-in): 0 = the reference's stateless chunks; -1 = stateful streaming (the
+    # session carries the vocoder's cross-chunk state: streamed PCM == non-streamed PCM at a per-chunk cost independent of the
+    # utterance length); c > 0 = c frames of left context decoded again in front of every streamed chunk and dropped.
     stream_left_context: int = 0
 
     def to_gen_config(self) -> L.GenConfig:

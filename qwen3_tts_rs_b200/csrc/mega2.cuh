@@ -211,13 +211,19 @@ __device__ __forceinline__ void prof2(const M2Args& a, int tag) {
 }
 
 // next GEMV phase's weight rows of this CTA -> L2 (they do not depend on activations)
+// a.prefetch 1 (default): one thread (lane 0 of warp 1) requests the whole range; 2 (Q3_PF_SPLIT=1): lane 0 of each of the
+// 16 warps requests one sixteenth -- an experiment: a single cp.async.bulk INTO SHARED MEMORY of 50-130 KB holds its issuing
+// thread for more than a microsecond (mega5.cuh), the L2 prefetch form does not (the split is 3 % slower).
 __device__ __forceinline__ void m2_prefetch(const M2Args& a, const M2Phase* nx) {
-  if (a.prefetch == 0 || nx == nullptr || threadIdx.x != 32) return;
+  if (a.prefetch == 0 || nx == nullptr) return;
+  if (a.prefetch == 1 ? threadIdx.x != 32 : (threadIdx.x & 31) != 0) return;
   int r0, r1;
   mega_row_range(nx->N, r0, r1);
   if (r1 <= r0) return;
-  l2_prefetch_bulk(nx->W + (size_t)r0 * nx->K, (size_t)(r1 - r0) * nx->K * 2);
-  if (nx->W2 != nullptr) l2_prefetch_bulk(nx->W2 + (size_t)r0 * nx->K, (size_t)(r1 - r0) * nx->K * 2);
+  size_t bytes = (size_t)(r1 - r0) * nx->K * 2, off = 0;
+  if (a.prefetch != 1) { bytes /= MEGA_WARPS; off = (size_t)(threadIdx.x >> 5) * bytes; }     // multiples of 64 bytes
+  l2_prefetch_bulk(reinterpret_cast<const char*>(nx->W + (size_t)r0 * nx->K) + off, bytes);
+  if (nx->W2 != nullptr) l2_prefetch_bulk(reinterpret_cast<const char*>(nx->W2 + (size_t)r0 * nx->K) + off, bytes);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -11,18 +11,21 @@
 //     warp caps every thread at 96 registers (5 warps per scheduler), and its weights are consumed slot by slot behind
 //     mbarrier waits inside the dependent part of the phase -- 4.30 ms per frame against 2.93.
 // This generation keeps what worked on each side:
-//   * NO extra warp (16 warps, 128 registers): the ring's producer is thread 0 itself, run as a coroutine -- one
-//     non-blocking step per iteration of the poll loop it spins in anyway while the other 511 threads sit at the barrier
-//     (m2_wait), and at every phase boundary;
-//   * a phase's fragments are copied from the ring into registers at the phase's ENTRY, before the wait (16 x LDS.128 per
-//     lane at most), and the slots are released at once: after the wait the phase is mega2's register-resident phase,
-//     instruction for instruction -- activations, MMAs from registers, one combine;
-//   * the slots released at the entry of phase j are refilled with the weights of phase j+1 during j's own barrier wait,
-//     so they land while j loads its activations and combines: four 32 KB slots suffice (the largest register-resident
-//     phase needs four), and a copy is one cp.async.bulk per tile when K = 1024 (the tile is contiguous) or per row;
+//   * NO extra warp (16 warps, 128 registers);
+//   * ONE prefetch buffer per CTA (all the shared memory mega2's work area leaves free, ~156 KB) holds the rows of the NEXT
+//     register-resident phase: a CTA's rows [r0, r1) x K are contiguous in global memory, so the fill is one bulk copy per
+//     matrix, split into sixteen so that every warp issues its own small piece (a single 50-130 KB cp.async.bulk holds the
+//     issuing thread for ~1.9 us);
+//   * a phase copies its fragments buffer -> registers at its ENTRY, before the wait (16 x LDS.128 per lane at most); the
+//     block barrier that ends the wait proves every warp has done so, and right after it the warps issue the next ring
+//     phase's rows into the same buffer (found by thread 0 scanning the descriptor ring, never past an undecided
+//     PROLOGUE).  After the wait the phase is mega2's register-resident phase, instruction for instruction;
 //   * the two big talker phases (gate/up, down: 340 / 170 KB per SM, bandwidth-bound) keep streaming global -> registers
 //     as in mega2.cuh; the 88 KB phase program moves out of shared memory (16-entry descriptor ring staged 8 phases ahead
-//     by warp 1), which is what makes room for the ring.
+//     by warp 1), which is what makes room for the buffer.
+// Result: bit-identical codes to mega2, deterministic, and SLOWER -- 4.22 ms per frame against 2.89 (1.7B, batch 8): the
+// buffer is full 0.3-0.4 us after a phase asks for it, but the extra shared-memory hop and the bulk traffic in flight
+// during the activation loads cost more than the shorter wait returns.  Opt-in (Q3_MEGA=5); kept as a measured result.
 #pragma once
 #include "mega4.cuh"
 

@@ -615,6 +615,12 @@ static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   a.err = s->host_flags_dev + 4;
   const char* e2 = std::getenv("Q3_PREFETCH");
   a.prefetch = e2 ? (std::atoi(e2) != 0) : 1;      // the plan itself is part of the program (m2_build_program)
+  {
+    // Q3_PF_SPLIT=1: the request is split over the 16 warps (m2_prefetch).  Measured 3 % SLOWER (2.99 vs 2.89 ms per frame,
+    // 1.7B batch 8): the L2 prefetch does not hold its issuing thread the way a bulk copy into shared memory does.
+    const char* e6 = std::getenv("Q3_PF_SPLIT");
+    if (a.prefetch && e6 && std::atoi(e6) != 0) a.prefetch = 2;
+  }
   const char* e3 = std::getenv("Q3_PF_SLEEP");
   a.pf_sleep = e3 ? std::atoi(e3) : 200;
   const char* e4 = std::getenv("Q3_RING_SHIFT");
