@@ -60,15 +60,17 @@ def gather_pcm(local_pcm, local_counts: Sequence[int], all_counts: Sequence[int]
     if n_local:
         w = min(smax, pcm.shape[1])
         buf[:n_local, :w] = pcm[:n_local, :w].to(device)
-    gathered = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, gathered, dst=dst)
+    # one receive buffer, one device -> host copy on `dst` (a copy per row would synchronise n_total times)
+    big = torch.empty((world, width, smax), dtype=torch.float32, device=device) if rank == dst else None
+    dist.gather(buf, list(big.unbind(0)) if rank == dst else None, dst=dst)
     if rank != dst:
         return None
+    host = big.cpu().numpy()
     out = []
     for r in range(world):
         lo, hi = shard_range(n_total, r, world)
         for j in range(hi - lo):
-            out.append(trim(gathered[r][j], all_counts[lo + j]))
+            out.append(np.ascontiguousarray(host[r, j, : int(all_counts[lo + j]) * samples_per_frame]))
     return out
 
 
