@@ -119,10 +119,29 @@ q3_status q3_prefill_embeds(q3_session* s, const uint16_t* embeds, const int32_t
  * which covers prefill_custom_voice / prefill_voice_design (src/models/talker.rs:451-491, 585-627). */
 q3_status q3_prefill_ids(q3_session* s, const int32_t* text_ids, const int32_t* codec_ids,
                          const int32_t* lens, int32_t l_max);
+/* Voice-clone prompt, x-vector only or with an in-context (ICL) reference (talker side: the speaker and
+ * speech encoders that produce `speaker_embeds` and `ref_codes` are out of scope).  As q3_prefill_ids, with two more kinds of
+ * codec part per position:
+ *   codec_ids[b][p] == Q3_POS_SPEAKER (-2)      : speaker_embeds[b] (bf16 [batch][hidden]), the continuous speaker embedding of
+ *                                                 prefill_voice_clone (src/models/talker.rs:511-564, position 7)
+ *   codec_ids[b][p] == Q3_POS_REF_FRAME(t)      : the 16-way embedding sum of reference frame t of row b,
+ *                                                 codec_embedding[c0] + code_predictor.codec_embedding[g-1][c_g], g = 1..15 in
+ *                                                 order (sum_ref_codec_embeddings, src/lib.rs:1239-1257)
+ * ref_codes: u32 [batch][t_ref_max][16], t_ref[batch] frames valid (NULL / 0 for x-vector only).  The reference runs the ICL
+ * block as a second causal chunk behind the 9-position prefill (src/lib.rs:953-987); one causal prefill over the
+ * concatenation fills the same KV cache and ends in the same last hidden state and logits, so the host mirror passes
+ * [prefill positions ++ build_icl_prompt positions (streaming overlay, src/models/talker.rs:684-704)] in one call. */
+#define Q3_POS_SPEAKER (-2)
+#define Q3_POS_REF_FRAME(t) (-16 - (t))
+q3_status q3_prefill_voice_clone(q3_session* s, const int32_t* text_ids, const int32_t* codec_ids, const int32_t* lens,
+                                 int32_t l_max, const uint16_t* speaker_embeds, const uint32_t* ref_codes,
+                                 const int32_t* t_ref, int32_t t_ref_max);
 /* ref: Qwen3TTS::build_trailing_text (src/lib.rs:508-519).  trailing: bf16 [batch][lt_max][hidden]. */
 q3_status q3_set_trailing_text(q3_session* s, const uint16_t* trailing, const int32_t* lt, int32_t lt_max,
                                const uint16_t* tts_pad /*[hidden]*/);
-/* Same from token ids: rows are text_proj(ids[b][0..n-1]) ++ text_proj(tts_eos); pad = text_proj(tts_pad). */
+/* Same from token ids: rows are text_proj(ids[b][0..n-1]) ++ text_proj(tts_eos); pad = text_proj(tts_pad).
+ * n[b] == -1: no trailing rows at all -- every frame adds tts_pad (an ICL prompt that consumed the whole text,
+ * src/models/talker.rs:691-703). */
 q3_status q3_set_trailing_ids(q3_session* s, const int32_t* ids, const int32_t* n, int32_t n_max,
                               int32_t tts_eos_id, int32_t tts_pad_id);
 

@@ -9,6 +9,7 @@
  *   Qwen3TTS::synthesize_with_voice       ref: src/lib.rs:718-784   (token ids in: tokenisation is outside the path)
  *   Qwen3TTS::synthesize_voice_design     ref: src/lib.rs:802-870
  *   Qwen3TTS::generate_codes              ref: src/lib.rs:530-656
+ *   Qwen3TTS::synthesize_voice_clone      ref: src/lib.rs:895-1060  (speaker embedding / reference codes in: the encoders are outside the path)
  *   Qwen3TTS::decode_codes                ref: src/lib.rs:881-890
  *   Qwen3TTS::synthesize_streaming        ref: src/lib.rs:1070-1093 -> StreamingSession (src/lib.rs:1484-1782)
  *   SynthesisOptions                      ref: src/lib.rs:1786-1836
@@ -207,6 +208,14 @@ inline int16_t pcm_f32_to_i16(float x) {
   if (std::isnan(x)) return 0;
   float c = x < -1.0f ? -1.0f : (x > 1.0f ? 1.0f : x);
   return (int16_t)(c * 32767.0f);
+}
+
+/* f32 -> bf16 bits, round to nearest even (what Tensor::to_dtype(BF16) does to the speaker embedding, lib.rs:930) */
+inline uint16_t f32_to_bf16_bits(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);   // NaN stays NaN
+  return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
 }
 
 struct AudioBuffer {  // ref: src/audio/io.rs:27-33
@@ -805,6 +814,20 @@ class Session {
       for (int p = 0; p < lens[b]; ++p) { ti[(size_t)b * lmax + p] = text[b][p]; ci[(size_t)b * lmax + p] = codec[b][p]; }
     check(q3_prefill_ids(h_, ti.data(), ci.data(), lens.data(), lmax));
   }
+  /* batch-1 voice-clone prefill (ref: prefill_voice_clone talker.rs:511-564 ++ build_icl_prompt talker.rs:646-705): codec parts
+     may be Q3_POS_SPEAKER / Q3_POS_REF_FRAME(t); speaker: bf16 bits [hidden]; ref_codes: [t_ref][16] or empty */
+  void prefill_voice_clone(const std::vector<int32_t>& text, const std::vector<int32_t>& codec, const std::vector<uint16_t>& speaker,
+                           const std::vector<uint32_t>& ref_codes) {
+    if (batch_ != 1) throw Error(Q3_ERR_INVALID, "prefill_voice_clone: one utterance per session in this mirror");
+    const int32_t len = (int32_t)text.size(), t_ref = (int32_t)(ref_codes.size() / 16);
+    check(q3_prefill_voice_clone(h_, text.data(), codec.data(), &len, len, speaker.data(), ref_codes.empty() ? nullptr : ref_codes.data(),
+                                 &t_ref, t_ref));
+  }
+  /* no trailing rows at all: every frame adds tts_pad (an ICL prompt that consumed the whole text, talker.rs:691-703) */
+  void set_trailing_none(int32_t tts_eos_id, int32_t tts_pad_id) {
+    std::vector<int32_t> n(batch_, -1), buf(batch_, 0);
+    check(q3_set_trailing_ids(h_, buf.data(), n.data(), 1, tts_eos_id, tts_pad_id));
+  }
   /* ref: build_trailing_text, lib.rs:508-519 */
   void set_trailing_ids(const std::vector<std::vector<int32_t>>& ids, int32_t tts_eos_id, int32_t tts_pad_id) {
     std::vector<int32_t> n(batch_);
@@ -898,6 +921,47 @@ inline Prompt voice_design_prompt(int32_t text_vocab, const std::vector<int32_t>
   for (int32_t c : {tok::CODEC_THINK, tok::CODEC_THINK_BOS, (int32_t)lang, tok::CODEC_THINK_EOS, tok::CODEC_PAD}) p.codec.push_back(c);
   if (!text_ids.empty()) { p.text.push_back(text_ids[0]); p.codec.push_back(tok::CODEC_BOS); }
   return p;
+}
+
+/* ref: VoiceClonePrompt, lib.rs:127-134.  speaker_embedding: f32 [hidden]; ref_codes: [T_ref][16] (ICL mode) */
+struct VoiceClonePrompt {
+  std::vector<float> speaker_embedding;
+  std::optional<FrameCodes> ref_codes;
+  std::optional<std::vector<int32_t>> ref_text_ids;
+  bool is_icl() const { return ref_codes.has_value() && ref_text_ids.has_value(); }
+};
+constexpr int32_t ICL_MIN_FRAMES = 75, ICL_FRAMES_PER_TOKEN = 6;   // lib.rs:1472-1475
+constexpr double ICL_MIN_REPETITION_PENALTY = 1.5;                 // lib.rs:1478
+struct ClonePrompt {
+  Prompt p;
+  std::vector<int32_t> trailing;   // ids for set_trailing_ids (tts_eos is appended there)
+  bool no_trailing = false;        // ICL prompt that consumed the whole text: every frame adds tts_pad
+};
+/* ref: prefill_voice_clone (talker.rs:511-564) followed, in ICL mode, by the streaming overlay of build_icl_prompt
+   (talker.rs:646-705; lib.rs:953-987 runs it as a second causal chunk -- one causal prefill over the concatenation is the same
+   computation). */
+inline ClonePrompt voice_clone_prompt(int32_t text_vocab, const std::vector<int32_t>& text_ids, const VoiceClonePrompt& vc, Language lang) {
+  auto sid = [&](int32_t t) { return special_text_id(text_vocab, t); };
+  ClonePrompt c;
+  c.p.text = {sid(tok::IM_START), sid(tok::ASSISTANT), sid(tok::NEWLINE), sid(tok::TTS_PAD), sid(tok::TTS_PAD), sid(tok::TTS_PAD),
+              sid(tok::TTS_PAD), sid(tok::TTS_PAD), sid(tok::TTS_BOS)};
+  c.p.codec = {-1, -1, -1, tok::CODEC_THINK, tok::CODEC_THINK_BOS, (int32_t)lang, tok::CODEC_THINK_EOS, Q3_POS_SPEAKER, tok::CODEC_PAD};
+  if (!vc.is_icl()) {
+    if (!text_ids.empty()) { c.p.text.push_back(text_ids[0]); c.p.codec.push_back(tok::CODEC_BOS); }
+    c.trailing.assign(text_ids.size() > 1 ? text_ids.begin() + 1 : text_ids.end(), text_ids.end());
+    return c;
+  }
+  std::vector<int32_t> all_text = *vc.ref_text_ids;
+  all_text.insert(all_text.end(), text_ids.begin(), text_ids.end());
+  all_text.push_back(sid(tok::TTS_EOS));
+  const int32_t n_text = (int32_t)all_text.size(), n_codec = (int32_t)vc.ref_codes->size() + 1;
+  for (int32_t i = 0; i < n_codec; ++i) {
+    c.p.text.push_back(i < n_text ? all_text[i] : sid(tok::TTS_PAD));
+    c.p.codec.push_back(i == 0 ? (int32_t)tok::CODEC_BOS : Q3_POS_REF_FRAME(i - 1));
+  }
+  if (n_text > n_codec) c.trailing.assign(all_text.begin() + n_codec, all_text.end() - 1);
+  else c.no_trailing = true;
+  return c;
 }
 
 // ---- facade ---------------------------------------------------------------------------------------------------------------
@@ -1002,6 +1066,42 @@ class Qwen3TTS {
   /* ref: synthesize_streaming, lib.rs:1070-1093. */
   StreamingSession synthesize_streaming(const std::vector<int32_t>& input_ids, Speaker sp, Language lang, const SynthesisOptions& o) const {
     return StreamingSession(new_session({input_ids}, {custom_voice_prompt(tv(), input_ids, sp, lang)}, o, {seed_of(o)}, o.max_length));
+  }
+  /* ref: synthesize_voice_clone / synthesize_voice_clone_debug, lib.rs:895-1060: ICL adjustments of the generation config
+     (913-927), voice-clone prefill + ICL block, frame loop, and in ICL mode the reference frames decoded in front of the
+     generated ones with ref_len / total_len of the waveform cut from its start (1021-1040). */
+  AudioBuffer synthesize_voice_clone(const std::vector<int32_t>& input_ids, const VoiceClonePrompt& vc, Language lang,
+                                     const SynthesisOptions& options, FrameCodes* codes_out = nullptr) const {
+    SynthesisOptions o = options;
+    if ((int32_t)vc.speaker_embedding.size() != model_->desc().hidden) throw Error(Q3_ERR_INVALID, "speaker embedding must have `hidden` elements");
+    if (vc.is_icl()) {
+      o.repetition_penalty = std::max(o.repetition_penalty, ICL_MIN_REPETITION_PENALTY);
+      o.max_length = std::min(o.max_length, std::max(ICL_MIN_FRAMES, (int32_t)input_ids.size() * ICL_FRAMES_PER_TOKEN));
+    }
+    const ClonePrompt cp = voice_clone_prompt(tv(), input_ids, vc, lang);
+    const int32_t max_seq = std::max(o.max_length + 256, (int32_t)cp.p.text.size() + o.max_length);
+    Session sess(*model_, 1, max_seq, o, {seed_of(o)});
+    std::vector<uint16_t> spk(vc.speaker_embedding.size());
+    for (size_t i = 0; i < spk.size(); ++i) spk[i] = f32_to_bf16_bits(vc.speaker_embedding[i]);
+    std::vector<uint32_t> ref;
+    if (vc.is_icl())
+      for (const auto& fr : *vc.ref_codes) {
+        if (fr.size() != 16) throw Error(Q3_ERR_INVALID, "reference frames are 16 codes wide");
+        ref.insert(ref.end(), fr.begin(), fr.end());
+      }
+    sess.prefill_voice_clone(cp.p.text, cp.p.codec, spk, ref);
+    const int32_t eos = special_text_id(tv(), tok::TTS_EOS), pad = special_text_id(tv(), tok::TTS_PAD);
+    if (cp.no_trailing) sess.set_trailing_none(eos, pad);
+    else sess.set_trailing_ids({cp.trailing}, eos, pad);
+    FrameCodes codes = sess.generate(o.max_length)[0];
+    if (codes_out) *codes_out = codes;
+    if (!vc.is_icl()) return decode_codes(codes);
+    FrameCodes combined = *vc.ref_codes;
+    combined.insert(combined.end(), codes.begin(), codes.end());
+    AudioBuffer audio = decode_codes(combined);
+    const size_t cut = vc.ref_codes->size() * audio.samples.size() / std::max<size_t>(1, combined.size());
+    audio.samples.erase(audio.samples.begin(), audio.samples.begin() + std::min(cut, audio.samples.size()));
+    return audio;
   }
   /* ref: decode_codes, lib.rs:881-890. */
   AudioBuffer decode_codes(const FrameCodes& codes) const {

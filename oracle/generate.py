@@ -128,7 +128,7 @@ def prefill_and_generate(talker: Talker, cp: CodePredictor, prefill_embeds: torc
 def follow(talker: Talker, cp: CodePredictor, prefill_embeds: torch.Tensor, text_ids: Sequence[int],
            cfg: smp.GenerationConfig, seed: int, frames: Sequence[Sequence[int]],
            first_logits: Optional[np.ndarray] = None, frame_logits: Optional[Sequence[np.ndarray]] = None,
-           kv_max: Optional[int] = None, text_rows=None) -> dict:
+           kv_max: Optional[int] = None, text_rows=None, trailing_override: Optional[torch.Tensor] = None) -> dict:
     """Test aid (no reference counterpart): the loop of generate_codes (lib.rs:530-656) FOLLOWING a trajectory produced
     elsewhere.  `frames[f] = [tok, c0..c14]` are the codes the CUDA path emitted; every decision input (semantic token,
     acoustic codes fed to the next code-predictor pass, penalty mask) is taken from them, every tensor is this oracle's
@@ -147,6 +147,9 @@ def follow(talker: Talker, cp: CodePredictor, prefill_embeds: torch.Tensor, text
     penalty_mask = np.zeros((1, vocab), dtype=np.float32)
     ctx = smp.SamplingContext(seed)
     trailing, tlen, pad = talker.build_trailing_text(text_ids)
+    if trailing_override is not None:
+        # voice-clone ICL mode (lib.rs:953-987): the trailing text is what build_icl_prompt left over, [1, Lt, H]
+        trailing, tlen = trailing_override.to(torch.float32), int(trailing_override.shape[1])
     out_text = dict(trailing=trailing.clone(), pad=pad.clone())
     if text_rows is not None:
         # (trailing [1, tlen, H], pad [1, 1, H]) as the OTHER side projected them: the talker-input add (lib.rs:617-621) is then

@@ -295,6 +295,43 @@ class Talker:
             hidden = torch.cat([hidden, first], 1)
         return hidden
 
+    def voice_clone_embeds(self, text_tokens: Sequence[int], speaker_embed: torch.Tensor, language_id: int, icl_mode: bool):
+        """prefill_voice_clone input assembly (talker.rs:511-564): prefill_custom_voice with the discrete speaker token
+        replaced by a continuous speaker embedding [hidden]; in ICL mode the (first text + codec_bos) position is omitted
+        (9 positions instead of 10)."""
+        p = self.p
+        pre = self.codec_embed([S.CODEC_THINK, S.CODEC_THINK_BOS, language_id, S.CODEC_THINK_EOS])
+        spk = p.r(speaker_embed.to(torch.float32)).reshape(1, 1, self.spec.hidden)     # cast to the compute dtype (lib.rs:930)
+        suf = self.codec_embed([S.CODEC_PAD, S.CODEC_BOS])
+        codec = torch.cat([pre, spk, suf], 1)
+        hidden = torch.cat([self._role_prefix(), p.r(self._tts_pad_bos(5) + codec[:, :6])], 1)
+        if not icl_mode and len(text_tokens) > 0:
+            first = p.r(self.projected_text(text_tokens[:1]) + codec[:, 6:7])
+            hidden = torch.cat([hidden, first], 1)
+        return hidden
+
+    def build_icl_prompt(self, target_text_ids: Sequence[int], ref_text_ids: Sequence[int], ref_codec_embeds: torch.Tensor,
+                         non_streaming: bool = False):
+        """TalkerModel::build_icl_prompt (talker.rs:646-705) -> (icl_embed [1, L, H], trailing [1, Lt, H]).
+        Text side: text_proj([ref_text ++ target_text ++ tts_eos]); codec side: [codec_bos ++ ref_codec_embeds].
+        Streaming form (the one lib.rs:960-963 calls): element-wise overlay over the codec length; the text that does not
+        fit becomes the trailing text, otherwise the text is padded with tts_pad and the trailing text is tts_pad alone."""
+        p = self.p
+        all_text = list(ref_text_ids) + list(target_text_ids) + [special_id(self.spec, S.TTS_EOS)]
+        text = self.projected_text(all_text)
+        n_text = text.shape[1]
+        codec = torch.cat([self.codec_embed([S.CODEC_BOS]), ref_codec_embeds.to(torch.float32)], 1)
+        n_codec = codec.shape[1]
+        pad = self.tts_pad_embed()
+        if non_streaming:
+            text_cp = p.r(text + self.codec_embed([S.CODEC_PAD]).expand(1, n_text, -1))
+            codec_tp = p.r(codec + pad.expand(1, n_codec, -1))
+            return torch.cat([text_cp, codec_tp], 1), pad
+        if n_text > n_codec:
+            return p.r(text[:, :n_codec] + codec), text[:, n_codec:]
+        padded = torch.cat([text, pad.expand(1, n_codec - n_text, -1)], 1) if n_codec > n_text else text
+        return p.r(padded + codec), pad
+
     def _rope(self, positions):
         return rope_cos_sin(positions, self.spec.head_dim, self.spec.rope_theta)
 
@@ -379,9 +416,45 @@ class CodePredictor:
             return codes, torch.cat(all_logits, 1)[0]
         return codes
 
+    def embed_codes_for_group(self, group: int, codes: Sequence[int]) -> torch.Tensor:
+        """CodePredictor::embed_codes_for_group: rows of codec_embeddings[group] -> [1, T, H_talker]."""
+        return self.codec_embeddings[group][torch.tensor(list(codes), dtype=torch.long)][None]
+
     def acoustic_embeddings_sum(self, codes: Sequence[int]):
         """code_predictor.rs:497-519: acc = E0[c0]; acc += Ei[ci] in order (each add rounded)."""
         acc = self.codec_embeddings[0][codes[0]][None, None]
         for i in range(1, len(codes)):
             acc = self.p.r(acc + self.codec_embeddings[i][codes[i]][None, None])
         return acc
+
+
+def sum_ref_codec_embeddings(talker: Talker, cp: "CodePredictor", ref_codes: Sequence[Sequence[int]]) -> torch.Tensor:
+    """Qwen3TTS::sum_ref_codec_embeddings (lib.rs:1239-1257): per reference frame, talker.codec_embedding[c0] plus the
+    code predictor's embedding of group g for c_g, g = 1..15, added in that order (each add rounded) -> [1, T, H]."""
+    p = talker.p
+    codes = [list(map(int, fr)) for fr in ref_codes]
+    summed = talker.codec_embed([fr[0] for fr in codes])
+    for g in range(1, 16):
+        summed = p.r(summed + cp.embed_codes_for_group(g - 1, [fr[g] for fr in codes]))
+    return summed
+
+
+# lib.rs:1472-1478
+ICL_MIN_FRAMES = 75
+ICL_FRAMES_PER_TOKEN = 6
+ICL_MIN_REPETITION_PENALTY = 1.5
+
+
+def voice_clone_prompt(talker: Talker, cp: "CodePredictor", text_ids: Sequence[int], speaker_embed: torch.Tensor, language_id: int,
+                       ref_codes=None, ref_text_ids=None):
+    """The prompt side of synthesize_voice_clone (lib.rs:895-1003): -> (prefill_embeds [1, L, H], trailing [1, Lt, H]).
+    The reference prefills 9 (ICL) or 10 positions and, in ICL mode, runs the ICL block as a second causal chunk at offset 9
+    (lib.rs:953-987); causal attention makes that identical to one prefill over the concatenation, which is what is
+    returned here.  Trailing text: the ICL remainder (or tts_pad alone) in ICL mode, build_trailing_text otherwise."""
+    is_icl = ref_codes is not None and ref_text_ids is not None
+    hidden = talker.voice_clone_embeds(text_ids, speaker_embed, language_id, is_icl)
+    if not is_icl:
+        return hidden, talker.build_trailing_text(text_ids)[0]
+    ref = sum_ref_codec_embeddings(talker, cp, ref_codes)
+    icl, trailing = talker.build_icl_prompt(text_ids, ref_text_ids, ref, non_streaming=False)
+    return torch.cat([hidden, icl], 1), trailing

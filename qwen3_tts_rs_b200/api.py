@@ -108,6 +108,30 @@ class AudioBuffer:
         self.samples = formats.normalize_db(self.samples, target_db)
 
 
+@dataclass
+class VoiceClonePrompt:
+    """VoiceClonePrompt (lib.rs:127-134).  The encoders that produce it (ECAPA-TDNN speaker encoder, Mimi speech encoder) are
+    out of scope here: the speaker embedding and the reference codes enter as data."""
+    speaker_embedding: torch.Tensor                     # [hidden]
+    ref_codes: Optional[np.ndarray] = None              # [T_ref, 16] codec codes of the reference audio (ICL mode)
+    ref_text_ids: Optional[Sequence[int]] = None        # tokenized reference transcript (ICL mode)
+
+    @property
+    def is_icl(self) -> bool:
+        return self.ref_codes is not None and self.ref_text_ids is not None
+
+
+# lib.rs:1472-1478
+ICL_MIN_FRAMES = 75
+ICL_FRAMES_PER_TOKEN = 6
+ICL_MIN_REPETITION_PENALTY = 1.5
+POS_SPEAKER = -2                                        # Q3_POS_SPEAKER
+
+
+def pos_ref_frame(t: int) -> int:                       # Q3_POS_REF_FRAME(t)
+    return -16 - t
+
+
 def codes_to_tensor(codes: Sequence[Sequence[int]]) -> np.ndarray:
     """src/lib.rs:1417-1431: [n_frames][16] u32 -> i64 [1,16,T], data[q*T + f] = codes[f][q]."""
     n = len(codes)
@@ -212,6 +236,29 @@ class Session:
             ci[b, : lens[b]] = codec_ids[b]
         L.check(self.lib.q3_prefill_ids(self.handle, _ptr(ti), _ptr(ci), _ptr(lens), lmax))
 
+    def prefill_voice_clone(self, text_ids: Sequence[Sequence[int]], codec_ids: Sequence[Sequence[int]],
+                            speaker_embeds: Sequence[torch.Tensor], ref_codes: Sequence[Optional[np.ndarray]]):
+        """q3_prefill_voice_clone: as prefill_ids with Q3_POS_SPEAKER / Q3_POS_REF_FRAME(t) codec parts; speaker_embeds[b]
+        [hidden] (stored bf16), ref_codes[b] u32 [T_ref, 16] or None."""
+        H = self.model.spec.hidden
+        lens = np.array([len(t) for t in text_ids], dtype=np.int32)
+        lmax = int(lens.max())
+        ti = np.full((self.B, lmax), -1, dtype=np.int32)
+        ci = np.full((self.B, lmax), -1, dtype=np.int32)
+        for b in range(self.B):
+            ti[b, : lens[b]] = text_ids[b]
+            ci[b, : lens[b]] = codec_ids[b]
+        spk = torch.zeros(self.B, H, dtype=torch.bfloat16)
+        for b, e in enumerate(speaker_embeds):
+            spk[b] = e.reshape(H).to(torch.bfloat16)
+        t_ref = np.array([0 if r is None else len(r) for r in ref_codes], dtype=np.int32)
+        tmax = int(t_ref.max())
+        rc = np.zeros((self.B, max(1, tmax), 16), dtype=np.uint32)
+        for b, r in enumerate(ref_codes):
+            if r is not None and len(r):
+                rc[b, : len(r)] = np.asarray(r, dtype=np.uint32)
+        L.check(self.lib.q3_prefill_voice_clone(self.handle, _ptr(ti), _ptr(ci), _ptr(lens), lmax, _ptr(spk), _ptr(rc), _ptr(t_ref), tmax))
+
     def set_trailing_text(self, trailing: Sequence[torch.Tensor], tts_pad: torch.Tensor):
         H = self.model.spec.hidden
         lt = np.array([t.shape[0] for t in trailing], dtype=np.int32)
@@ -225,11 +272,13 @@ class Session:
     def set_trailing_ids(self, ids: Sequence[Sequence[int]]):
         """Rows = text_proj(ids[b]) ++ tts_eos; pad = text_proj(tts_pad)  (lib.rs:508-519)."""
         sp = self.model.spec
-        n = np.array([len(t) for t in ids], dtype=np.int32)
+        # ids[b] is None: no trailing rows at all (every frame adds tts_pad) -- an ICL prompt that consumed the text
+        n = np.array([-1 if t is None else len(t) for t in ids], dtype=np.int32)
         nmax = max(1, int(n.max()))
         buf = np.zeros((self.B, nmax), dtype=np.int32)
         for b, t in enumerate(ids):
-            buf[b, : len(t)] = t
+            if t is not None:
+                buf[b, : len(t)] = t
         L.check(self.lib.q3_set_trailing_ids(self.handle, _ptr(buf), _ptr(n), nmax,
                                              S.special_text_id(sp, S.TTS_EOS), S.special_text_id(sp, S.TTS_PAD)))
 
@@ -470,6 +519,76 @@ class Qwen3TTS:
             text.append(int(text_ids[0]))
             codec.append(S.CODEC_BOS)
         return text, codec
+
+    def voice_clone_prompt(self, text_ids: Sequence[int], prompt: VoiceClonePrompt, language: str):
+        """Position-wise (text id, codec part) pairs of prefill_voice_clone (talker.rs:511-564) followed, in ICL mode, by the
+        streaming overlay of build_icl_prompt (talker.rs:646-705; the reference runs it as a second causal chunk, lib.rs:953-987
+        -- one causal prefill over the concatenation is the same computation).  -> (text, codec, trailing ids or None):
+        trailing ids are what set_trailing_ids takes (it appends tts_eos); None = no trailing rows, every frame adds tts_pad."""
+        sp = self.spec
+        sid = lambda t: S.special_text_id(sp, t)
+        text = [sid(S.IM_START), sid(S.ASSISTANT), sid(S.NEWLINE)] + [sid(S.TTS_PAD)] * 5 + [sid(S.TTS_BOS)]
+        codec = [-1, -1, -1, S.CODEC_THINK, S.CODEC_THINK_BOS, S.LANGUAGE_IDS[language], S.CODEC_THINK_EOS, POS_SPEAKER, S.CODEC_PAD]
+        text_ids = [int(t) for t in text_ids]
+        if not prompt.is_icl:
+            if len(text_ids) > 0:
+                text.append(text_ids[0])
+                codec.append(S.CODEC_BOS)
+            return text, codec, text_ids[1:]
+        all_text = [int(t) for t in prompt.ref_text_ids] + text_ids + [sid(S.TTS_EOS)]
+        n_text, n_codec = len(all_text), len(prompt.ref_codes) + 1
+        for i in range(n_codec):
+            text.append(all_text[i] if i < n_text else sid(S.TTS_PAD))
+            codec.append(S.CODEC_BOS if i == 0 else pos_ref_frame(i - 1))
+        trailing = all_text[n_codec:-1] if n_text > n_codec else None      # the remainder ends in tts_eos, which set_trailing_ids appends
+        return text, codec, trailing
+
+    def generate_codes_voice_clone(self, batch_text_ids, prompts: Sequence[VoiceClonePrompt], language: str = "english",
+                                   options: Optional[SynthesisOptions] = None, seeds=None):
+        """The code-generation half of synthesize_voice_clone_debug (lib.rs:895-1017) for a batch: ICL adjustments of the
+        generation config (repetition penalty >= 1.5, frame budget min(max_length, max(75, 6 x text tokens)), lib.rs:913-927),
+        voice-clone prefill (+ ICL block), trailing text, frame loop.  -> list of FrameCodes."""
+        import dataclasses
+        options = options or SynthesisOptions()
+        icl = [p.is_icl for p in prompts]
+        if any(icl) != all(icl):
+            raise ValueError("a batch must be all-ICL or all x-vector-only (the repetition penalty differs)")
+        budgets = [min(options.max_length, max(ICL_MIN_FRAMES, len(t) * ICL_FRAMES_PER_TOKEN)) if p.is_icl else options.max_length
+                   for t, p in zip(batch_text_ids, prompts)]
+        if all(icl):
+            options = dataclasses.replace(options, repetition_penalty=max(options.repetition_penalty, ICL_MIN_REPETITION_PENALTY))
+        pp = [self.voice_clone_prompt(t, p, language) for t, p in zip(batch_text_ids, prompts)]
+        mf = max(budgets)
+        B = len(prompts)
+        sess = Session(self.model, B, dataclasses.replace(options, max_length=mf), self._seeds(options, B, seeds),
+                       max_seq=max(len(p[0]) for p in pp) + mf + 8)
+        try:
+            sess.prefill_voice_clone([p[0] for p in pp], [p[1] for p in pp], [p.speaker_embedding for p in prompts],
+                                     [p.ref_codes if p.is_icl else None for p in prompts])
+            sess.set_trailing_ids([p[2] for p in pp])
+            codes, n = sess.generate(mf)
+            # rows are independent: a row whose own budget is below the batch's is cut there, as its own run would have been
+            return [codes[b, : min(int(n[b]), budgets[b])].tolist() for b in range(B)]
+        finally:
+            sess.close()
+
+    def synthesize_voice_clone(self, batch_text_ids, prompts: Sequence[VoiceClonePrompt], language: str = "english",
+                               options: Optional[SynthesisOptions] = None, seeds=None):
+        """synthesize_voice_clone (lib.rs:895-1060): in ICL mode the reference frames are decoded in front of the generated
+        ones and ref_len / total_len of the waveform is cut from its start (lib.rs:1021-1040)."""
+        all_codes = self.generate_codes_voice_clone(batch_text_ids, prompts, language, options, seeds)
+        out = []
+        for codes, p in zip(all_codes, prompts):
+            if p.is_icl:
+                ref = [[int(c) for c in fr] for fr in np.asarray(p.ref_codes)]
+                combined = ref + codes
+                audio = self.decode_codes(combined)
+                cut = len(ref) * len(audio) // max(1, len(combined))
+                audio.samples = audio.samples[min(cut, len(audio)):]
+                out.append(audio)
+            else:
+                out.append(self.decode_codes(codes))
+        return out
 
     def _new_session(self, batch_text_ids, prompts, options: SynthesisOptions, seeds, max_seq=None) -> Session:
         sess = Session(self.model, len(batch_text_ids), options, seeds, max_seq)

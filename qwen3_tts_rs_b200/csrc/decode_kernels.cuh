@@ -394,6 +394,38 @@ __global__ void assemble_embeds_kernel(const bf16* __restrict__ text_proj, const
   }
 }
 
+// Voice-clone prompt assembly (prefill_voice_clone talker.rs:511-564, build_icl_prompt streaming overlay talker.rs:684-704,
+// sum_ref_codec_embeddings lib.rs:1239-1257).  As assemble_embeds_kernel, with two more kinds of codec part:
+//   codec_id == -2       : the row's continuous speaker embedding (speaker[b], bf16 [B][H])
+//   codec_id <= -16      : the 16-way embedding sum of reference frame t = -16 - codec_id of row b:
+//                          E_talker[c0] + E_cp0[c1] + ... + E_cp14[c15], added in that order, each add rounded to bf16
+// One bf16 rounding for (text part + codec part) when both are present.  l_max = positions per row (t = b * l_max + p).
+struct RefTables { const bf16* e[16]; };
+__global__ void assemble_embeds_ex_kernel(const bf16* __restrict__ text_proj, const int* __restrict__ text_ids,
+                                          const int* __restrict__ codec_ids, RefTables tab, const bf16* __restrict__ speaker,
+                                          const uint32_t* __restrict__ ref_codes, int t_ref_max, int l_max, int H,
+                                          bf16* __restrict__ out) {
+  const int t = blockIdx.x, b = t / l_max;
+  const int ti = text_ids[t], ci = codec_ids[t];
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float cv = 0.f;
+    const bool has_c = ci >= 0 || ci == -2 || ci <= -16;
+    if (ci >= 0) cv = bf2f(tab.e[0][(size_t)ci * H + c]);
+    else if (ci == -2) cv = bf2f(speaker[(size_t)b * H + c]);
+    else if (ci <= -16) {
+      const uint32_t* codes = ref_codes + ((size_t)b * t_ref_max + (-16 - ci)) * 16;
+      cv = bf2f(tab.e[0][(size_t)codes[0] * H + c]);
+#pragma unroll
+      for (int g = 1; g < 16; ++g) cv = rbf(cv + bf2f(tab.e[g][(size_t)codes[g] * H + c]));
+    }
+    float v = 0.f;
+    if (ti >= 0 && has_c) v = rbf(bf2f(text_proj[(size_t)t * H + c]) + cv);
+    else if (ti >= 0) v = bf2f(text_proj[(size_t)t * H + c]);
+    else if (has_c) v = cv;
+    out[(size_t)t * H + c] = f2bf(v);
+  }
+}
+
 __global__ void gather_rows_kernel(const bf16* __restrict__ table, const int* __restrict__ ids, int H, int n_rows_table,
                                    bf16* __restrict__ out) {
   const int t = blockIdx.x;

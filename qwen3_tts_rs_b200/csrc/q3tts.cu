@@ -70,6 +70,7 @@ struct q3_session {
   int mega_ver = 2;                // 1: fence-based grid barriers (mega.cuh), 2: tagged dataflow phases (mega2.cuh)
   DBuf tr_ids, tr_proj;            // staging of q3_set_trailing_ids
   DBuf pf_tid, pf_cid;             // staging of q3_prefill_ids
+  DBuf pf_spk, pf_ref;             // q3_prefill_voice_clone: speaker embeddings, reference codes
   DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag;
   std::vector<DBuf> m2_progs;      // cached full-frame program of every row group
   std::vector<int> m2_group_nph;
@@ -1341,6 +1342,57 @@ q3_status q3_prefill_ids(q3_session* s, const int32_t* text_ids, const int32_t* 
   Q3_API_END
 }
 
+q3_status q3_prefill_voice_clone(q3_session* s, const int32_t* text_ids, const int32_t* codec_ids, const int32_t* lens, int32_t l_max,
+                                 const uint16_t* speaker_embeds, const uint32_t* ref_codes, const int32_t* t_ref, int32_t t_ref_max) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && text_ids && codec_ids && lens && l_max >= 1 && t_ref_max >= 0, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(!s->prefilled, Q3_ERR_STATE, "session already prefilled; call q3_session_reset first");
+  Q3_REQUIRE(s->m->text_emb, Q3_ERR_MISSING_WEIGHT, "Missing weight: talker.model.text_embedding.weight");
+  Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
+  const q3_model_desc& d = s->m->d;
+  const int B = s->B, T = B * l_max, H = d.hidden;
+  Q3_REQUIRE(d.groups == 16, Q3_ERR_UNSUPPORTED, "reference frames are 16 codes wide");
+  for (int b = 0; b < B; ++b) {
+    Q3_REQUIRE(lens[b] >= 1 && lens[b] <= l_max, Q3_ERR_INVALID, "prompt length out of range");
+    const int tr = (t_ref && t_ref_max > 0) ? t_ref[b] : 0;
+    Q3_REQUIRE(tr >= 0 && tr <= t_ref_max, Q3_ERR_INVALID, "reference length out of range");
+    for (int p = 0; p < l_max; ++p) {
+      const int ti = text_ids[(size_t)b * l_max + p], ci = codec_ids[(size_t)b * l_max + p];
+      Q3_REQUIRE(ti < d.text_vocab && ci < d.codec_vocab, Q3_ERR_INVALID, "token id out of range");
+      if (p >= lens[b]) continue;
+      if (ci == -2) Q3_REQUIRE(speaker_embeds != nullptr, Q3_ERR_INVALID, "speaker position without speaker embeddings");
+      else if (ci <= -16) Q3_REQUIRE(ref_codes != nullptr && -16 - ci < tr, Q3_ERR_INVALID, "reference frame index out of range");
+      else Q3_REQUIRE(ci >= -1, Q3_ERR_INVALID, "unknown codec-part kind");
+    }
+    for (int f = 0; f < tr; ++f)
+      for (int g = 0; g < 16; ++g) {
+        const uint32_t c = ref_codes[((size_t)b * t_ref_max + f) * 16 + g];
+        Q3_REQUIRE(c < (uint32_t)(g == 0 ? d.codec_vocab : d.cp_vocab), Q3_ERR_INVALID, "reference code out of range");
+      }
+  }
+  ensure_scratch(s, T);
+  DBuf& tid = s->pf_tid;
+  DBuf& cid = s->pf_cid;
+  tid.ensure((size_t)T * 4); cid.ensure((size_t)T * 4);
+  Q3_CHECK_CUDA(cudaMemcpyAsync(tid.p, text_ids, T * 4, cudaMemcpyHostToDevice, s->st));
+  Q3_CHECK_CUDA(cudaMemcpyAsync(cid.p, codec_ids, T * 4, cudaMemcpyHostToDevice, s->st));
+  s->pf_spk.ensure((size_t)B * H * 2);
+  if (speaker_embeds) Q3_CHECK_CUDA(cudaMemcpyAsync(s->pf_spk.p, speaker_embeds, (size_t)B * H * 2, cudaMemcpyHostToDevice, s->st));
+  s->pf_ref.ensure(std::max<size_t>(16, (size_t)B * t_ref_max * 16 * 4));
+  if (ref_codes && t_ref_max > 0)
+    Q3_CHECK_CUDA(cudaMemcpyAsync(s->pf_ref.p, ref_codes, (size_t)B * t_ref_max * 16 * 4, cudaMemcpyHostToDevice, s->st));
+  text_project(s, tid.as<int>(), T, s->sc.o.as<bf16>());
+  RefTables tab;
+  tab.e[0] = s->m->codec_emb;
+  for (int g = 1; g < 16; ++g) tab.e[g] = s->m->cp_emb[g - 1];
+  assemble_embeds_ex_kernel<<<T, 256, 0, s->st>>>(s->sc.o.as<bf16>(), tid.as<int>(), cid.as<int>(), tab, s->pf_spk.as<bf16>(),
+                                                  s->pf_ref.as<uint32_t>(), t_ref_max, l_max, H, s->sc.x.as<bf16>());
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  prefill_run(s, lens, l_max);
+  Q3_API_END
+}
+
 q3_status q3_set_trailing_text(q3_session* s, const uint16_t* trailing, const int32_t* lt, int32_t lt_max, const uint16_t* tts_pad) {
   Q3_API_BEGIN
   Q3_REQUIRE(s && trailing && lt && tts_pad && lt_max >= 1, Q3_ERR_INVALID, "bad argument");
@@ -1373,7 +1425,8 @@ q3_status q3_set_trailing_ids(q3_session* s, const int32_t* ids, const int32_t* 
   // rows: ids[b][0..n-1] ++ tts_eos (lib.rs:508-516); one extra row at the end for tts_pad
   std::vector<int> all((size_t)B * lt_max + 1, tts_pad_id), lt(B);
   for (int b = 0; b < B; ++b) {
-    Q3_REQUIRE(n[b] >= 0 && n[b] <= n_max, Q3_ERR_INVALID, "trailing length out of range");
+    Q3_REQUIRE(n[b] >= -1 && n[b] <= n_max, Q3_ERR_INVALID, "trailing length out of range");
+    if (n[b] < 0) { lt[b] = 0; continue; }     // no trailing rows at all: every frame adds tts_pad (ICL prompt that consumed the text)
     for (int i = 0; i < n[b]; ++i) {
       int id = ids[(size_t)b * n_max + i];
       Q3_REQUIRE(id >= 0 && id < d.text_vocab, Q3_ERR_INVALID, "text id out of range");

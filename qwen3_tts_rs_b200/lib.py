@@ -27,7 +27,7 @@ EXPORTS = [
     "q3_last_error", "q3_abi_version", "q3_kernel_launch_count",
     "q3_model_create", "q3_model_set_tensor", "q3_model_finalize", "q3_model_destroy",
     "q3_session_create", "q3_session_reset", "q3_session_destroy", "q3_session_stream", "q3_session_synchronize",
-    "q3_prefill_embeds", "q3_prefill_ids", "q3_set_trailing_text", "q3_set_trailing_ids",
+    "q3_prefill_embeds", "q3_prefill_ids", "q3_prefill_voice_clone", "q3_set_trailing_text", "q3_set_trailing_ids",
     "q3_generate", "q3_generate_async", "q3_get_codes", "q3_stream_next", "q3_session_set_stream_context",
     "q3_vocoder_decode", "q3_vocode_session",
     "q3_talker_step", "q3_code_predictor_frame", "q3_sample",
@@ -118,6 +118,7 @@ def load() -> C.CDLL:
     lib.q3_session_synchronize.argtypes = [vp]
     lib.q3_prefill_embeds.argtypes = [vp, vp, vp, i32]
     lib.q3_prefill_ids.argtypes = [vp, vp, vp, vp, i32]
+    lib.q3_prefill_voice_clone.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32]
     lib.q3_set_trailing_text.argtypes = [vp, vp, vp, i32, vp]
     lib.q3_set_trailing_ids.argtypes = [vp, vp, vp, i32, i32, i32]
     lib.q3_generate.argtypes = [vp, i32, vp, vp]

@@ -256,6 +256,62 @@ impl<'a> B200Session<'a> {
         Ok(s)
     }
 
+    /// Voice-clone session (src/lib.rs:895-1003): `prefill_voice_clone` (src/models/talker.rs:511-564) followed, in ICL
+    /// mode, by the streaming overlay of `build_icl_prompt` (talker.rs:646-705) -- passed as ONE causal prefill, which fills the
+    /// same KV cache and ends in the same last hidden state / logits as the reference's two chunks.  `speaker_bf16`: the
+    /// speaker embedding cast to bf16 bits (lib.rs:930); `ref_codes`: `[T_ref][16]` (ICL) or empty.  The caller applies the
+    /// ICL adjustments of the generation config (lib.rs:913-927) to `options` first.
+    pub fn new_voice_clone(model: &'a B200Model, input_ids: &[u32], speaker_bf16: &[u16], ref_codes: &[[u32; 16]],
+                           ref_text_ids: Option<&[u32]>, language: i32, options: &SynthesisOptions) -> Result<Self> {
+        const POS_SPEAKER: i32 = -2; // Q3_POS_SPEAKER
+        let pos_ref = |t: usize| -16 - t as i32; // Q3_POS_REF_FRAME(t)
+        let mut text = vec![IM_START, ASSISTANT, NEWLINE, TTS_PAD, TTS_PAD, TTS_PAD, TTS_PAD, TTS_PAD, TTS_BOS];
+        let mut codec = vec![-1, -1, -1, CODEC_THINK, CODEC_THINK_BOS, language, CODEC_THINK_EOS, POS_SPEAKER, CODEC_PAD];
+        let mut trailing: Option<Vec<i32>> = Some(input_ids.iter().skip(1).map(|&t| t as i32).collect());
+        if let Some(ref_text) = ref_text_ids {
+            let mut all: Vec<i32> = ref_text.iter().chain(input_ids.iter()).map(|&t| t as i32).collect();
+            all.push(TTS_EOS);
+            let n_codec = ref_codes.len() + 1;
+            for i in 0..n_codec {
+                text.push(if i < all.len() { all[i] } else { TTS_PAD });
+                codec.push(if i == 0 { CODEC_BOS } else { pos_ref(i - 1) });
+            }
+            // the text that did not fit is the trailing text (it ends in tts_eos, which q3_set_trailing_ids appends);
+            // otherwise there are no trailing rows and every frame adds tts_pad
+            trailing = if all.len() > n_codec { Some(all[n_codec..all.len() - 1].to_vec()) } else { None };
+        } else if let Some(&first) = input_ids.first() {
+            text.push(first as i32);
+            codec.push(CODEC_BOS);
+        }
+        let seed = options.seed.ok_or_else(|| anyhow!("the B200 backend needs SynthesisOptions.seed (reproducible runs only)"))?;
+        let cfg = ffi::q3_gen_config {
+            max_new_tokens: options.max_length as i32,
+            temperature: options.temperature,
+            top_k: options.top_k as i32,
+            top_p: options.top_p,
+            repetition_penalty: options.repetition_penalty,
+            eos_token_id: options.eos_token_id.map(|t| t as i32).unwrap_or(-1),
+            min_new_tokens: options.min_new_tokens as i32,
+            chunk_frames: options.chunk_frames as i32,
+        };
+        let max_seq = (options.max_length + 256).max(text.len() + options.max_length) as i32;
+        let mut raw = ptr::null_mut();
+        ffi::check(unsafe { ffi::q3_session_create(model.raw, 1, max_seq, &cfg, &seed, &mut raw) })?;
+        let s = Self { raw, model, chunk_frames: options.chunk_frames.max(1), frames_generated: 0, done: false };
+        let (len, t_ref) = (text.len() as i32, ref_codes.len() as i32);
+        let ref_ptr = if ref_codes.is_empty() { ptr::null() } else { ref_codes.as_ptr() as *const u32 };
+        ffi::check(unsafe {
+            ffi::q3_prefill_voice_clone(s.raw, text.as_ptr(), codec.as_ptr(), &len, len, speaker_bf16.as_ptr(), ref_ptr, &t_ref, t_ref)
+        })?;
+        let (n, padded) = match trailing {
+            Some(t) if !t.is_empty() => (t.len() as i32, t),
+            Some(_) => (0, vec![0i32]),
+            None => (-1, vec![0i32]),
+        };
+        ffi::check(unsafe { ffi::q3_set_trailing_ids(s.raw, padded.as_ptr(), &n, padded.len() as i32, TTS_EOS, TTS_PAD) })?;
+        Ok(s)
+    }
+
     /// `generate_codes` (src/lib.rs:530-656): the whole loop runs on the device; one read-back at the end.
     pub fn generate(&mut self, max_frames: usize) -> Result<FrameCodes> {
         let mut codes = vec![0u32; max_frames * 16];

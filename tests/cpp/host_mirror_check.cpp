@@ -42,6 +42,22 @@ int main(int argc, char** argv) {
       std::printf("speaker_unknown %d\n", (int)speaker_from_name("nobody").has_value());
       return 0;
     }
+    if (mode == "clone_prompt") {  // clone_prompt <text_vocab> <text ids> <ref text ids | -> <ref frames>: voice-clone id layout
+      const int32_t tv = (int32_t)std::stol(argv[2]);
+      const auto ids = parse_ids(argv[3]);
+      VoiceClonePrompt vc;
+      vc.speaker_embedding.assign(8, 0.f);
+      const int32_t t_ref = (int32_t)std::stol(argv[5]);
+      if (std::string(argv[4]) != "-") {
+        vc.ref_text_ids = parse_ids(argv[4]);
+        vc.ref_codes = FrameCodes((size_t)t_ref, std::vector<uint32_t>(16, 1u));
+      }
+      const ClonePrompt c = voice_clone_prompt(tv, ids, vc, *language_from_name("english"));
+      print_ids("text", c.p.text); print_ids("codec", c.p.codec); print_ids("trailing", c.trailing);
+      std::printf("no_trailing %d\n", (int)c.no_trailing);
+      std::printf("bf16 %04x %04x %04x\n", f32_to_bf16_bits(1.0f), f32_to_bf16_bits(0.3f), f32_to_bf16_bits(-2.0078125f));
+      return 0;
+    }
     if (mode == "formats") {  // formats <dir>: write the dump / WAV formats from deterministic data, read Python's files back
       const std::string d = argv[2];
       FrameCodes codes;

@@ -55,6 +55,25 @@ def test_prompts_match_the_python_mirror(exe, spec):
         assert len(cv[0]) == (10 if ids else 9)                    # talker.rs:437-449
 
 
+def test_voice_clone_prompts_match_the_python_mirror(exe):
+    """prefill_voice_clone ++ build_icl_prompt id layout (talker.rs:511-564, 646-705): x-vector only, ICL with a text remainder,
+    ICL with padded text; and the f32 -> bf16 rounding applied to the speaker embedding."""
+    spec = S.SPEC_TINY
+    t = api.Qwen3TTS.__new__(api.Qwen3TTS)
+    t.spec = spec
+    ids = [11, 12, 13, 14, 15]
+    for ref_text, t_ref in ((None, 0), ([21, 22, 23], 4), ([21], 30)):
+        vc = api.VoiceClonePrompt(torch.zeros(spec.hidden), None if ref_text is None else np.ones((t_ref, 16), np.uint32), ref_text)
+        text, codec, trailing = t.voice_clone_prompt(ids, vc, "english")
+        out = _lines(run(exe, "clone_prompt", spec.text_vocab, ",".join(map(str, ids)),
+                         "-" if ref_text is None else ",".join(map(str, ref_text)), t_ref))
+        assert [int(x) for x in out["text"].split()] == text and [int(x) for x in out["codec"].split()] == codec
+        assert out["no_trailing"] == ("1" if trailing is None else "0")
+        assert [int(x) for x in out["trailing"].split()] == (trailing or [])
+    bits = lambda f: int(torch.tensor([f]).to(torch.bfloat16).view(torch.int16).item()) & 0xffff
+    assert out["bf16"].split() == [f"{bits(1.0):04x}", f"{bits(0.3):04x}", f"{bits(-2.0078125):04x}"]
+
+
 def test_formats_are_byte_identical(exe, tmp_path):
     d = str(tmp_path)
     codes = [[(f * 131 + q * 17) % 3072 for q in range(16)] for f in range(5)]

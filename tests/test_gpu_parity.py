@@ -56,14 +56,21 @@ def close_to_f32(cuda, bf, f32, what, stats):
                                       f"rms(bf16 - f32) {sigma:.4g} (tensor rms {rms:.4g})")
 
 
-def run_tapped(tts, prompts, seeds, opts, frames, instruct=None):
-    if instruct is None:
-        pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
-    else:       # VoiceDesign prefill (talker.rs:585-627): the instruct ids sit in front of the role prefix
-        pp = [tts.voice_design_prompt(t, ins, "english") for t, ins in zip(prompts, instruct)]
-    sess = tts._new_session(prompts, pp, opts, seeds, max_seq=max(len(p[0]) for p in pp) + frames + 40)
+def run_tapped(tts, prompts, seeds, opts, frames, instruct=None, clone=None):
+    if clone is not None:     # voice clone (talker.rs:511-564, 646-705): speaker embedding, optional ICL reference
+        pp = [tts.voice_clone_prompt(t, c, "english") for t, c in zip(prompts, clone)]
+        sess = api.Session(tts.model, len(prompts), opts, seeds, max_seq=max(len(p[0]) for p in pp) + frames + 40)
+        sess.prefill_voice_clone([p[0] for p in pp], [p[1] for p in pp], [c.speaker_embedding for c in clone],
+                                 [c.ref_codes if c.is_icl else None for c in clone])
+        sess.set_trailing_ids([p[2] for p in pp])
+    else:
+        if instruct is None:
+            pp = [tts.custom_voice_prompt(t, "ryan", "english") for t in prompts]
+        else:       # VoiceDesign prefill (talker.rs:585-627): the instruct ids sit in front of the role prefix
+            pp = [tts.voice_design_prompt(t, ins, "english") for t, ins in zip(prompts, instruct)]
+        sess = tts._new_session(prompts, pp, opts, seeds, max_seq=max(len(p[0]) for p in pp) + frames + 40)
     try:
-        text = sess.trailing_rows(cap=max(len(t) for t in prompts) + 1)
+        text = sess.trailing_rows(cap=max([len(t) for t in prompts] + [len(p[2] or []) for p in pp if len(p) > 2]) + 1)
         codes, n, taps = sess.generate_tapped(frames)
         taps["text"] = text
     finally:
@@ -71,11 +78,12 @@ def run_tapped(tts, prompts, seeds, opts, frames, instruct=None):
     return [codes[b, : n[b]].tolist() for b in range(len(prompts))], taps
 
 
-def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, taps=None, models=None, models32=None, instruct=None):
+def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, taps=None, models=None, models32=None, instruct=None,
+                 clone=None):
     """Runs the tapped CUDA loop (unless given) and holds rows `rows` to the oracle as the module docstring says.
     Returns a report dict (counts only; every violation asserts)."""
     if tapped is None:
-        tapped, taps = run_tapped(tts, prompts, seeds, opts, frames, instruct)
+        tapped, taps = run_tapped(tts, prompts, seeds, opts, frames, instruct, clone)
     tk, cp = models if models is not None else oracle_models(spec)
     tk32, cp32 = models32 if models32 is not None else oracle_models(spec, bf16=False)
     cfg = oracle_cfg(opts)
@@ -83,23 +91,35 @@ def check_follow(spec, tts, prompts, seeds, opts, frames, rows, tapped=None, tap
     for b in rows:
         got = tapped[b]
         n = len(got)
-        def prefill_embeds(t):
+        def prefill_embeds(t, c):
+            """-> (prefill embeddings, trailing-text override or None) of oracle talker t / code predictor c"""
+            if clone is not None:
+                from oracle import model as OM
+                pr = clone[b]
+                emb_, tr_ = OM.voice_clone_prompt(t, c, prompts[b], pr.speaker_embedding, S.LANGUAGE_IDS["english"],
+                                                  pr.ref_codes if pr.is_icl else None, pr.ref_text_ids if pr.is_icl else None)
+                return emb_, (tr_ if pr.is_icl else None)
             if instruct is None:
-                return t.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"])
-            return t.voice_design_embeds(prompts[b], instruct[b], S.LANGUAGE_IDS["english"])
-        emb = prefill_embeds(tk)
+                return t.custom_voice_embeds(prompts[b], S.SPEAKER_IDS["ryan"], S.LANGUAGE_IDS["english"]), None
+            return t.voice_design_embeds(prompts[b], instruct[b], S.LANGUAGE_IDS["english"]), None
+        emb, tr_over = prefill_embeds(tk, cp)
         kv_max = int(emb.shape[1]) + frames + 64
         tr_rows, tr_lt, tr_pad = taps["text"]
         gpu_text = (tr_rows[b, : int(tr_lt[b])][None], tr_pad[None, None])
+        if int(tr_lt[b]) == 0:      # no trailing rows on the device (ICL prompt consumed the text) == the reference's [tts_pad]
+            gpu_text = (tr_pad[None, None], tr_pad[None, None])
         fo = OG.follow(tk, cp, emb, prompts[b], cfg, seeds[b], got, first_logits=taps["first_logits"][b],
-                       frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=kv_max, text_rows=gpu_text)
+                       frame_logits=[taps["logits"][f, b] for f in range(n)], kv_max=kv_max, text_rows=gpu_text,
+                       trailing_override=tr_over)
         # the device's text projection (trailing rows + tts_pad) vs the oracle's: the same noise-calibrated bar as the logits
         o_tr = torch.cat([fo["text"]["trailing"][0], fo["text"]["pad"][0]], 0)
         g_tr = torch.cat([gpu_text[0][0].float(), gpu_text[1][0].float()], 0)
+        emb32, tr_over32 = prefill_embeds(tk32, cp32)
         f_tr32, f_len, f_pad32 = tk32.build_trailing_text(prompts[b])
+        if tr_over32 is not None:
+            f_tr32 = tr_over32
         close_to_f32(g_tr, o_tr, torch.cat([f_tr32[0], f_pad32[0]], 0), f"trailing text rows row {b}", rep)
-        emb32 = prefill_embeds(tk32)
-        f32 = OG.follow(tk32, cp32, emb32, prompts[b], cfg, seeds[b], got, kv_max=kv_max)      # noise calibration (item 5)
+        f32 = OG.follow(tk32, cp32, emb32, prompts[b], cfg, seeds[b], got, kv_max=kv_max, trailing_override=tr_over32)      # noise calibration (item 5)
         # 1. RNG stream
         assert [int(x) for x in taps["rng"][: n + 1, b]] == fo["rng_states"], ("rng stream", b)
         # 2. sampler replay on the CUDA path's own logits
@@ -255,3 +275,32 @@ def test_long_context_voice_design_prefill_follows_the_oracle():
     rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=(0, 1), tapped=tapped, taps=taps, instruct=instruct)
     print("follow report:", rep)
     assert rep["frames"] == 2 * F and rep["sample_exempt"] == 0
+
+
+@pytest.mark.parametrize("spec", [S.SPEC_TINY_PROJ, S.SPEC_0_6B], ids=["tiny_proj", "0.6b"])
+def test_voice_clone_prompts_follow_the_oracle(spec):
+    """SURVEY 8(f) row 4, talker side: voice-clone prefill with a continuous speaker embedding (talker.rs:511-564) and the ICL
+    block (sum_ref_codec_embeddings lib.rs:1239-1257 + build_icl_prompt talker.rs:646-705, run here as part of one causal
+    prefill).  Batch 3: x-vector only; ICL whose text outlasts the reference codes (trailing = the text remainder); ICL whose
+    reference codes outlast the text (text padded with tts_pad, no trailing rows).  Same six follow-mode checks."""
+    F = 3
+    opts = api.SynthesisOptions(max_length=F, repetition_penalty=1.5)
+    g = torch.Generator().manual_seed(2024)
+    H = spec.hidden
+    hi = min(151643, spec.text_vocab - 300) if spec.text_vocab > 4096 else spec.text_vocab
+    rnd_ids = lambda n: torch.randint(0, hi, (n,), generator=g).tolist()
+    def ref_codes(t):
+        c = torch.randint(0, 2048, (t, 16), generator=g).numpy().astype(np.uint32)
+        return c
+    spk = lambda: (torch.randn(H, generator=g) * 0.05)
+    prompts = [rnd_ids(9), rnd_ids(14), rnd_ids(4)]
+    clone = [api.VoiceClonePrompt(spk()),
+             api.VoiceClonePrompt(spk(), ref_codes(6), rnd_ids(5)),          # n_text = 5 + 14 + 1 = 20 > n_codec = 7
+             api.VoiceClonePrompt(spk(), ref_codes(12), rnd_ids(3))]         # n_text = 3 + 4 + 1 = 8 < n_codec = 13
+    seeds = [5, 6, 7]
+    tts = gpu_tts(spec)
+    # the batch API refuses to mix ICL and x-vector rows (different repetition penalties); sessions themselves do not care
+    tapped, taps = run_tapped(tts, prompts, seeds, opts, F, clone=clone)
+    rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=(0, 1, 2), tapped=tapped, taps=taps, clone=clone)
+    print("follow report:", rep)
+    assert rep["frames"] == 3 * F and rep["sample_exempt"] == 0

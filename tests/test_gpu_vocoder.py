@@ -145,3 +145,31 @@ def test_synthesize_with_voice_end_to_end():
     audio, timing = tts.synthesize_with_voice(prompts, options=api.SynthesisOptions(max_length=8), seeds=[1, 2], with_timing=True)
     assert all(len(a) == 8 * 1920 for a in audio)
     assert timing.generation_frames == 8 and timing.generation_ms > 0 and timing.decode_ms > 0
+
+
+def test_synthesize_voice_clone_budget_and_cut_rule():
+    """synthesize_voice_clone (lib.rs:895-1060) through the mirror: ICL rows get the reference's frame budget
+    min(max_length, max(75, 6 x text tokens)) and repetition penalty >= 1.5 (lib.rs:913-927); the reference frames are decoded
+    in front of the generated ones and ref_len / total_len of the waveform is cut from its start (lib.rs:1021-1040); an
+    x-vector-only batch decodes the generated frames alone; a mixed batch is refused."""
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    g = torch.Generator().manual_seed(8)
+    spk = lambda: torch.randn(spec.hidden, generator=g) * 0.05
+    ref = lambda t: torch.randint(0, 2048, (t, 16), generator=g).numpy().astype(np.uint32)
+    texts = [W.synthetic_prompt(0, spec)[:4], W.synthetic_prompt(1, spec)[:15]]
+    icl = [api.VoiceClonePrompt(spk(), ref(5), [3, 4, 5]), api.VoiceClonePrompt(spk(), ref(9), [6, 7])]
+    opts = api.SynthesisOptions(max_length=80, eos_token_id=None)
+    codes = tts.generate_codes_voice_clone(texts, icl, options=opts, seeds=[1, 2])
+    assert [len(c) for c in codes] == [75, 80]           # max(75, 6*4) = 75 ; min(80, max(75, 6*15)) = 80
+    audio = tts.synthesize_voice_clone(texts, icl, options=opts, seeds=[1, 2])
+    for a, c, p in zip(audio, codes, icl):
+        total = (len(p.ref_codes) + len(c)) * 1920
+        assert len(a) == total - len(p.ref_codes) * total // (len(p.ref_codes) + len(c))
+    # row 0 alone (batch 1, its own 75-frame budget) gives the same codes: rows are independent
+    assert tts.generate_codes_voice_clone(texts[:1], icl[:1], options=opts, seeds=[1])[0] == codes[0]
+    xv = [api.VoiceClonePrompt(spk()), api.VoiceClonePrompt(spk())]
+    audio = tts.synthesize_voice_clone(texts, xv, options=api.SynthesisOptions(max_length=6, eos_token_id=None), seeds=[1, 2])
+    assert all(len(a) == 6 * 1920 for a in audio)
+    with pytest.raises(ValueError):
+        tts.generate_codes_voice_clone(texts, [icl[0], xv[0]], options=opts)

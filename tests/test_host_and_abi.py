@@ -92,6 +92,57 @@ def test_prompt_id_lists_mirror_the_oracle_embeddings():
     assert len(text) == 9                      # no text token -> no 10th position (talker.rs:484-488)
 
 
+def test_voice_clone_prompt_lists_mirror_the_oracle_embeddings():
+    """voice_clone_prompt (x-vector only, ICL with a text remainder, ICL with padded text): the (text id, codec part) pairs,
+    with Q3_POS_SPEAKER and Q3_POS_REF_FRAME(t) parts resolved as the CUDA kernel resolves them, add up to the oracle's
+    prefill_voice_clone ++ build_icl_prompt embeddings bit for bit, and the trailing ids to its trailing text."""
+    import numpy as np
+    import torch
+    from oracle import model as OM
+    from conftest import talker_weights
+    spec = S.SPEC_TINY_PROJ
+    w = talker_weights(spec)
+    tk, cp = OM.Talker(spec, w, OM.BF16P), OM.CodePredictor(spec, w, OM.BF16P)
+    tts = api.Qwen3TTS.__new__(api.Qwen3TTS)
+    tts.spec = spec
+    g = torch.Generator().manual_seed(3)
+    spk = torch.randn(spec.hidden, generator=g) * 0.05
+    r = OM.BF16P.r
+
+    def embed(text, codec, prompt):
+        rows = []
+        for t, c in zip(text, codec):
+            ce = None
+            if c >= 0:
+                ce = tk.codec_embedding[c]
+            elif c == api.POS_SPEAKER:
+                ce = r(spk.float())
+            elif c <= -16:
+                fr = [int(x) for x in prompt.ref_codes[-16 - c]]
+                ce = tk.codec_embedding[fr[0]]
+                for gi in range(1, 16):
+                    ce = r(ce + cp.codec_embeddings[gi - 1][fr[gi]])
+            e = tk.projected_text([t])[0, 0] if t >= 0 else None
+            rows.append(ce if e is None else (e if ce is None else r(e + ce)))
+        return torch.stack(rows)[None]
+
+    ids = W.synthetic_prompt(4, spec)
+    lang = S.LANGUAGE_IDS["english"]
+    for ref_t, ref_text in ((None, None), (5, [11, 12, 13]), (40, [11, 12])):
+        rc = None if ref_t is None else torch.randint(0, 2048, (ref_t, 16), generator=g).numpy().astype(np.uint32)
+        prompt = api.VoiceClonePrompt(spk, rc, ref_text)
+        text, codec, trailing = tts.voice_clone_prompt(ids, prompt, "english")
+        emb, tr = OM.voice_clone_prompt(tk, cp, ids, spk, lang, rc, ref_text)
+        assert len(text) == len(codec) == emb.shape[1]
+        assert torch.equal(embed(text, codec, prompt), emb)
+        if trailing is None:                       # no rows: every frame adds tts_pad, as the reference's [tts_pad] trailing does
+            assert torch.equal(tr, tk.tts_pad_embed())
+        else:
+            assert torch.equal(torch.cat([tk.projected_text(trailing), tk.tts_eos_embed()], 1), tr)
+    assert len(tts.voice_clone_prompt(ids, api.VoiceClonePrompt(spk), "english")[0]) == 10
+    assert len(tts.voice_clone_prompt(ids, api.VoiceClonePrompt(spk, np.zeros((5, 16), np.uint32), [1]), "english")[0]) == 9 + 6
+
+
 def test_synthesis_options_defaults_and_gen_config():
     o = api.SynthesisOptions()                 # lib.rs:1822-1836
     assert (o.max_length, o.temperature, o.top_k, o.top_p, o.repetition_penalty, o.eos_token_id, o.chunk_frames,

@@ -349,3 +349,47 @@ def test_fork_rules_of_the_gpu_parity_tests():
     got[1][g + 1] = (ref[1][g + 1] + 1) % 2048
     assert first_divergence_is_a_near_tie(got, ref, tr, cfg)[:2] == (1, False)
     assert first_divergence_is_a_near_tie(ref[:4], ref, tr, cfg)[1] is False       # a length mismatch is not a fork
+
+
+def test_voice_clone_prompt_shapes_and_overlay_rules():
+    """prefill_voice_clone (talker.rs:511-564: 10 positions, 9 in ICL mode; position 7 carries the continuous speaker embedding
+    under tts_pad) and build_icl_prompt (talker.rs:646-705): streaming overlay over the codec length with the text remainder as
+    trailing text, or tts_pad-padded text and a [tts_pad] trailing; non-streaming form = [text + codec_pad ++ codec + tts_pad]."""
+    from qwen3_tts_rs_b200 import spec as S, weights as W
+    spec = S.SPEC_TINY_PROJ
+    w = W.make_talker_weights(spec)
+    tk, cp = OM.Talker(spec, w, OM.F32P), OM.CodePredictor(spec, w, OM.F32P)
+    g = torch.Generator().manual_seed(0)
+    spk = torch.randn(spec.hidden, generator=g)
+    lang = S.LANGUAGE_IDS["english"]
+    ids = [5, 6, 7, 8]
+    xv = tk.voice_clone_embeds(ids, spk, lang, icl_mode=False)
+    icl9 = tk.voice_clone_embeds(ids, spk, lang, icl_mode=True)
+    assert xv.shape[1] == 10 and icl9.shape[1] == 9 and torch.equal(xv[:, :9], icl9)
+    assert torch.allclose(xv[0, 7], tk.tts_pad_embed()[0, 0] + spk, atol=1e-6)                    # speaker embedding under tts_pad
+    cv = tk.custom_voice_embeds(ids, S.SPEAKER_IDS["ryan"], lang)
+    keep = [i for i in range(10) if i != 7]
+    assert torch.equal(xv[0, keep], cv[0, keep])                                       # only the speaker position differs
+    ref = torch.randint(0, 2048, (6, 16), generator=g).tolist()
+    rce = OM.sum_ref_codec_embeddings(tk, cp, ref)
+    assert rce.shape == (1, 6, spec.hidden)
+    want0 = tk.codec_embedding[ref[0][0]] + sum(cp.codec_embeddings[gi - 1][ref[0][gi]] for gi in range(1, 16))
+    assert torch.allclose(rce[0, 0], want0, atol=1e-5)
+    eos = OM.special_id(spec, S.TTS_EOS)
+    # text (3 + 4 + 1 = 8) longer than codec (1 + 6 = 7): overlay 7 positions, 1 trailing row = tts_eos
+    emb, tr = tk.build_icl_prompt(ids, [1, 2, 3], rce)
+    assert emb.shape[1] == 7 and tr.shape[1] == 1 and torch.allclose(tr, tk.projected_text([eos]), atol=1e-6)
+    assert torch.allclose(emb[0, 0], tk.projected_text([1])[0, 0] + tk.codec_embedding[S.CODEC_BOS], atol=1e-6)
+    assert torch.allclose(emb[0, 3], tk.projected_text([5])[0, 0] + rce[0, 2], atol=1e-6)
+    # text (1 + 1 + 1 = 3) shorter: padded with tts_pad, trailing = [tts_pad]
+    emb, tr = tk.build_icl_prompt([5], [1], rce)
+    assert emb.shape[1] == 7 and torch.equal(tr, tk.tts_pad_embed())
+    assert torch.allclose(emb[0, 2], tk.projected_text([eos])[0, 0] + rce[0, 1], atol=1e-6)
+    assert torch.allclose(emb[0, 6], tk.tts_pad_embed()[0, 0] + rce[0, 5], atol=1e-6)
+    # non-streaming form
+    emb, tr = tk.build_icl_prompt(ids, [1, 2, 3], rce, non_streaming=True)
+    assert emb.shape[1] == 8 + 7 and torch.equal(tr, tk.tts_pad_embed())
+    assert torch.allclose(emb[0, 0], tk.projected_text([1])[0, 0] + tk.codec_embedding[S.CODEC_PAD], atol=1e-6)
+    assert torch.allclose(emb[0, 8], tk.codec_embedding[S.CODEC_BOS] + tk.tts_pad_embed()[0, 0], atol=1e-6)
+    full, tr = OM.voice_clone_prompt(tk, cp, ids, spk, lang, ref, [1, 2, 3])
+    assert full.shape[1] == 9 + 7
