@@ -119,6 +119,14 @@ q3_status q3_prefill_embeds(q3_session* s, const uint16_t* embeds, const int32_t
  * which covers prefill_custom_voice / prefill_voice_design (src/models/talker.rs:451-491, 585-627). */
 q3_status q3_prefill_ids(q3_session* s, const int32_t* text_ids, const int32_t* codec_ids,
                          const int32_t* lens, int32_t l_max);
+/* ECAPA-TDNN speaker encoder on a mel spectrogram (voice-clone front end).
+ * ref: SpeakerEncoder::forward (src/models/speaker.rs:448-476): initial TDNN, three squeeze-excitation Res2Net blocks, multi-layer
+ * feature aggregation, attentive statistics pooling, FC; raw (un-normalised) embedding.  Weights `speaker_encoder.*` (F32) through
+ * q3_model_set_tensor; dilations are the reference's config defaults (src/models/config.rs:144-146).  The mel front end
+ * (MelSpectrogram::compute_for_speaker_encoder, src/audio/mel.rs) stays on the host side of the boundary.
+ * mel: f32 [batch][mel_dim][t] (host); embed_out: f32 [batch][q3_speaker_embed_dim(m)] (host). */
+int32_t q3_speaker_embed_dim(const q3_model* m);
+q3_status q3_speaker_encode(const q3_model* m, const float* mel, int32_t batch, int32_t t, float* embed_out);
 /* Voice-clone prompt, x-vector only or with an in-context (ICL) reference (talker side: the speaker and
  * speech encoders that produce `speaker_embeds` and `ref_codes` are out of scope).  As q3_prefill_ids, with two more kinds of
  * codec part per position:

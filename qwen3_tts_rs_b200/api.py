@@ -164,7 +164,7 @@ class Model:
         self.finalized = False
 
     def set_tensor(self, name: str, t: torch.Tensor):
-        if name.startswith("decoder."):
+        if name.startswith(("decoder.", "speaker_encoder.")):       # the vocoder and the speaker encoder are F32 (lib.rs:344-345)
             h = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
             dt = L.Q3_F32
         else:
@@ -482,9 +482,15 @@ class Qwen3TTS:
         in `model_type` (None when the dimensions came from weight inspection, lib.rs:383-386)."""
         from . import formats
         ck = formats.load_checkpoint(model_id)
-        tts = cls.from_weights(ck.spec, ck.talker_weights, ck.vocoder_weights, device)
+        voc = dict(ck.vocoder_weights)
+        voc.update(ck.speaker_weights or {})          # F32 parts: vocoder + (Base checkpoints) the ECAPA speaker encoder
+        tts = cls.from_weights(ck.spec, ck.talker_weights, voc, device)
         tts.model_type = ck.config.model_type if ck.config is not None else None
         return tts
+
+    def supports_voice_cloning(self) -> bool:
+        """lib.rs:389-391: a speaker encoder was loaded."""
+        return int(self.model.lib.q3_speaker_embed_dim(self.model.handle)) > 0
 
     def supports_preset_speakers(self) -> bool:
         """lib.rs:393-404: CustomVoice only; permissive when the variant is unknown."""
@@ -660,6 +666,19 @@ class Qwen3TTS:
         prompts = [self.voice_design_prompt(text_ids, instruct_ids, language)]
         sess = self._new_session([text_ids], prompts, options, self._seeds(options, 1, None))
         return StreamingSession(self, sess)
+
+    def speaker_encode(self, mel: np.ndarray) -> torch.Tensor:
+        """SpeakerEncoder::forward (speaker.rs:448-476): mel spectrogram f32 [B, mel_dim, T] -> raw speaker embedding
+        f32 [B, enc_dim] (the VoiceClonePrompt.speaker_embedding).  Needs the speaker_encoder.* weights in the model; the
+        mel front end (src/audio/mel.rs) is the caller's."""
+        mel = np.ascontiguousarray(mel, dtype=np.float32)
+        B, _, T = mel.shape
+        dim = int(self.model.lib.q3_speaker_embed_dim(self.model.handle))
+        if dim <= 0:
+            raise L.Q3Error(5, "model has no finalized speaker-encoder weights")
+        out = np.zeros((B, dim), dtype=np.float32)
+        L.check(self.model.lib.q3_speaker_encode(self.model.handle, _ptr(mel), B, T, _ptr(out)))
+        return torch.from_numpy(out)
 
     def codes_to_tensor(self, codes):
         return codes_to_tensor(codes)

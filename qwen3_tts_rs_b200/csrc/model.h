@@ -106,6 +106,17 @@ struct VocoderW {
   VSnake final_snake;
 };
 
+// ECAPA-TDNN speaker encoder (speaker.rs:352-434).  k = 1 convs run on the vocoder's tensor-core conv kernels (VConv);
+// the reflect-padded k > 1 convs keep the checkpoint layout [Cout][Cin][k].
+struct SpkConv { const float* w = nullptr; const float* b = nullptr; int cout = 0, cin = 0, k = 1; };
+struct SpkBlock { VConv tdnn1, tdnn2, se1, se2; std::vector<SpkConv> branches; int dil = 1; };
+struct SpeakerW {
+  SpkConv init;
+  SpkBlock blk[3];
+  VConv mfa, asp_tdnn, asp_conv, fc;
+  int mel = 0, enc_dim = 0;
+};
+
 struct VocoderWorkspace {
   DBuf codes, e_first, e_rest, a, b, c, d, qh, kh, vh;
 };
@@ -144,8 +155,9 @@ struct q3_model {
   std::vector<LayerW> cl;
   const LayerW *tl_dev = nullptr, *cl_dev = nullptr;   // device copies of the layer tables (persistent kernel)
   const bf16 *cp_cos = nullptr, *cp_sin = nullptr;   // [cp_rope_positions][64]
-  bool has_talker = false, has_vocoder = false;
+  bool has_talker = false, has_vocoder = false, has_speaker = false;
   VocoderW voc;
+  SpeakerW spk;
   mutable std::mutex voc_mutex;          // guards voc_ws for the session-less q3_vocoder_decode
   mutable VocoderWorkspace voc_ws;
   mutable std::mutex pool_mutex;
@@ -169,6 +181,9 @@ struct q3_model {
 };
 
 void vocoder_finalize(q3_model* m);
+void speaker_finalize(q3_model* m);
+// mel: device f32 [mel_dim][T] (one utterance); out: device f32 [enc_dim].  ref: SpeakerEncoder::forward (speaker.rs:448-476)
+void speaker_run(const q3_model* m, const float* mel, int T, float* out, cudaStream_t st);
 // codes: device i64 [B][nq][T]; pcm: device f32 [B][T*upsample]
 void vocoder_run(const q3_model* m, VocoderWorkspace& ws, const long long* codes, int B, int T, float* pcm,
                  cudaStream_t st);

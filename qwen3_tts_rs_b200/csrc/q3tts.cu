@@ -873,7 +873,7 @@ q3_status q3_model_set_tensor(q3_model* m, const char* hf_name, const void* data
   }
   t.shape.assign(shape, shape + ndim);
   const size_t n = t.numel();
-  const bool is_voc = name.rfind("decoder.", 0) == 0;
+  const bool is_voc = name.rfind("decoder.", 0) == 0 || name.rfind("speaker_encoder.", 0) == 0;   // the F32 parts of the model
   const q3_dtype want = is_voc ? Q3_F32 : Q3_BF16;
   const size_t src_bytes = n * (dtype == Q3_BF16 ? 2 : 4);
   DBuf src;
@@ -986,7 +986,9 @@ q3_status q3_model_finalize(q3_model* m) {
   const q3_model_desc& d = m->d;
   const bool any_talker = m->t.count("talker.model.norm.weight") > 0;
   const bool any_voc = m->t.count("decoder.pre_conv.conv.weight") > 0;
-  Q3_REQUIRE(any_talker || any_voc, Q3_ERR_MISSING_WEIGHT, "Missing weight: no talker.* or decoder.* tensors were set");
+  const bool any_spk = m->t.count("speaker_encoder.blocks.0.conv.weight") > 0;
+  Q3_REQUIRE(any_talker || any_voc || any_spk, Q3_ERR_MISSING_WEIGHT,
+             "Missing weight: no talker.*, decoder.* or speaker_encoder.* tensors were set");
   if (any_talker) {
     m->codec_emb = needb(m, "talker.model.codec_embedding.weight");
     check_shape(need_bf16(m, "talker.model.codec_embedding.weight"), {d.codec_vocab, d.hidden}, "codec_embedding");
@@ -1035,6 +1037,7 @@ q3_status q3_model_finalize(q3_model* m) {
     m->has_talker = true;
   }
   if (any_voc) vocoder_finalize(m);
+  if (any_spk) speaker_finalize(m);
   Q3_CHECK_CUDA(cudaDeviceSynchronize());
   m->finalized = true;
   Q3_API_END
@@ -1681,6 +1684,26 @@ q3_status q3_vocoder_decode(const q3_model* m, const int64_t* codes, int32_t bat
   Q3_CHECK_CUDA(cudaMemcpy(dc.p, codes, dc.bytes, cudaMemcpyHostToDevice));
   vocoder_run(m, m->voc_ws, dc.as<long long>(), batch, t, dp.as<float>(), 0);
   Q3_CHECK_CUDA(cudaMemcpy(pcm, dp.p, (size_t)batch * t * up * 4, cudaMemcpyDeviceToHost));
+  Q3_API_END
+}
+
+int32_t q3_speaker_embed_dim(const q3_model* m) { return (m && m->finalized && m->has_speaker) ? m->spk.enc_dim : 0; }
+
+q3_status q3_speaker_encode(const q3_model* m, const float* mel, int32_t batch, int32_t t, float* embed_out) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(m && mel && embed_out && batch >= 0 && t >= 1, Q3_ERR_INVALID, "bad argument");
+  Q3_REQUIRE(m->finalized && m->has_speaker, Q3_ERR_STATE, "model has no finalized speaker-encoder weights");
+  Q3_CHECK_CUDA(cudaSetDevice(m->d.device));
+  std::lock_guard<std::mutex> lock(m->voc_mutex);
+  const size_t n_mel = (size_t)m->spk.mel * t;
+  DBuf dm, de;
+  dm.alloc(n_mel * 4);
+  de.alloc((size_t)m->spk.enc_dim * 4);
+  for (int b = 0; b < batch; ++b) {          // one utterance at a time, as SpeakerEncoder::encode is called (speaker.rs:436-445)
+    Q3_CHECK_CUDA(cudaMemcpy(dm.p, mel + (size_t)b * n_mel, n_mel * 4, cudaMemcpyHostToDevice));
+    speaker_run(m, dm.as<float>(), t, de.as<float>(), 0);
+    Q3_CHECK_CUDA(cudaMemcpy(embed_out + (size_t)b * m->spk.enc_dim, de.p, (size_t)m->spk.enc_dim * 4, cudaMemcpyDeviceToHost));
+  }
   Q3_API_END
 }
 

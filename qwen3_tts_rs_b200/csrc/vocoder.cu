@@ -9,6 +9,7 @@
 #include "vocoder_kernels.cuh"
 #include "vocoder_mma.cuh"
 #include "vocoder_umma.cuh"
+#include "speaker.cuh"
 
 namespace {
 
@@ -546,4 +547,122 @@ void vocoder_stream_chunk(const q3_model* m, VocoderWorkspace& ws, VocoderStream
                                   (size_t)Tb * sizeof(float), (size_t)B * Lt, cudaMemcpyDeviceToDevice, st));
   voc_back(m, w, B, Tb, pcm, st);
   ss.frames = f0 + T;
+}
+
+// ---- ECAPA-TDNN speaker encoder (voice-clone front end) ------------------------------------------------
+// ref: SpeakerEncoder::{new, forward} (src/models/speaker.rs:362-476).  Dilations are the reference's config defaults
+// (config.rs:144-146: 1, 2, 3, 4, 1 -- the published checkpoints use them; q3_model_desc carries no speaker section), every
+// other dimension is read from the weight shapes.
+namespace {
+SpkConv make_spk_conv(q3_model* m, const std::string& name) {
+  const RawTensor& w = need(m, name + ".weight");
+  Q3_REQUIRE(w.shape.size() == 3, Q3_ERR_INVALID, "conv weight must be 3-D: " + name);
+  SpkConv c;
+  c.w = w.buf.as<float>();
+  c.b = needp(m, name + ".bias");
+  c.cout = (int)w.shape[0]; c.cin = (int)w.shape[1]; c.k = (int)w.shape[2];
+  return c;
+}
+void launch_reflect_conv(const SpkConv& c, const float* xa, const float* xb, float* y, int dil, int T, cudaStream_t st) {
+  Q3_REQUIRE(dil * (c.k - 1) / 2 < T && dil * (c.k - 1) - dil * (c.k - 1) / 2 < T, Q3_ERR_INVALID,
+             "speaker encoder: the mel spectrogram is shorter than the reflect padding");
+  const size_t smem = (size_t)c.cin * c.k * sizeof(float);
+  Q3_REQUIRE(smem <= 48 * 1024, Q3_ERR_UNSUPPORTED, "speaker encoder: conv too wide for the staged weights");
+  spk_reflect_conv_relu_kernel<<<dim3(ceil_div(T, 128), c.cout), 128, smem, st>>>(xa, xb, c.w, c.b, y, c.cin, c.k, dil, T);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+}
+}  // namespace
+
+void speaker_finalize(q3_model* m) {
+  const std::string p = "speaker_encoder";
+  SpeakerW& s = m->spk;
+  const int dils[5] = {1, 2, 3, 4, 1};
+  s.init = make_spk_conv(m, p + ".blocks.0.conv");
+  s.mel = s.init.cin;
+  for (int i = 0; i < 3; ++i) {
+    const std::string b = p + ".blocks." + std::to_string(i + 1);
+    SpkBlock& k = s.blk[i];
+    k.dil = dils[i + 1];
+    k.tdnn1 = make_conv(m, b + ".tdnn1.conv.weight", b + ".tdnn1.conv.bias", false);
+    k.tdnn2 = make_conv(m, b + ".tdnn2.conv.weight", b + ".tdnn2.conv.bias", false);
+    k.se1 = make_conv(m, b + ".se_block.conv1.weight", b + ".se_block.conv1.bias", false);
+    k.se2 = make_conv(m, b + ".se_block.conv2.weight", b + ".se_block.conv2.bias", false);
+    Q3_REQUIRE(k.tdnn1.k == 1 && k.tdnn2.k == 1 && k.se1.k == 1 && k.se2.k == 1, Q3_ERR_UNSUPPORTED, "speaker encoder: 1x1 convs expected in " + b);
+    k.branches.clear();
+    for (int j = 0;; ++j) {
+      const std::string n = b + ".res2net_block.blocks." + std::to_string(j) + ".conv";
+      if (!m->t.count(n + ".weight")) break;
+      k.branches.push_back(make_spk_conv(m, n));
+    }
+    Q3_REQUIRE(!k.branches.empty() && k.branches[0].cout * ((int)k.branches.size() + 1) == k.tdnn1.cout, Q3_ERR_INVALID,
+               "speaker encoder: Res2Net branches do not tile the block's channels: " + b);
+  }
+  s.mfa = make_conv(m, p + ".mfa.conv.weight", p + ".mfa.conv.bias", false);
+  s.asp_tdnn = make_conv(m, p + ".asp.tdnn.conv.weight", p + ".asp.tdnn.conv.bias", false);
+  s.asp_conv = make_conv(m, p + ".asp.conv.weight", p + ".asp.conv.bias", false);
+  s.fc = make_conv(m, p + ".fc.weight", p + ".fc.bias", false);
+  Q3_REQUIRE(s.mfa.k == 1 && s.asp_tdnn.k == 1 && s.asp_conv.k == 1 && s.fc.k == 1, Q3_ERR_UNSUPPORTED, "speaker encoder: 1x1 convs expected (mfa / asp / fc)");
+  Q3_REQUIRE(s.mfa.cin == s.blk[0].tdnn1.cout + s.blk[1].tdnn1.cout + s.blk[2].tdnn1.cout && s.asp_tdnn.cin == 3 * s.mfa.cout &&
+                 s.asp_conv.cout == s.mfa.cout && s.fc.cin == 2 * s.mfa.cout, Q3_ERR_INVALID, "speaker encoder: inconsistent shapes");
+  s.enc_dim = s.fc.cout;
+  m->has_speaker = true;
+}
+
+void speaker_run(const q3_model* m, const float* mel, int T, float* out, cudaStream_t st) {
+  const SpeakerW& s = m->spk;
+  const int C0 = s.init.cout, Cm = s.mfa.cout, Ccat = s.mfa.cin;
+  int Cmax = C0;
+  for (int i = 0; i < 3; ++i) Cmax = std::max(Cmax, s.blk[i].tdnn1.cout);
+  DBuf h0, cat, t1, r2, t2, stat, se_a, se_b, hm, attn_in, a1, a2, pooled;
+  h0.alloc((size_t)C0 * T * 4); cat.alloc((size_t)Ccat * T * 4);
+  t1.alloc((size_t)Cmax * T * 4); r2.alloc((size_t)Cmax * T * 4); t2.alloc((size_t)Cmax * T * 4);
+  stat.alloc((size_t)2 * std::max(Cmax, Cm) * 4); se_a.alloc((size_t)Cmax * 4); se_b.alloc((size_t)Cmax * 4);
+  hm.alloc((size_t)Cm * T * 4); attn_in.alloc((size_t)3 * Cm * T * 4);
+  a1.alloc((size_t)s.asp_tdnn.cout * T * 4); a2.alloc((size_t)Cm * T * 4); pooled.alloc((size_t)2 * Cm * 4);
+  // blocks[0]: initial TDNN (speaker.rs:450)
+  launch_reflect_conv(s.init, mel, nullptr, h0.as<float>(), 1, T, st);
+  const float* x = h0.as<float>();
+  size_t cat_off = 0;
+  for (int i = 0; i < 3; ++i) {
+    const SpkBlock& k = s.blk[i];
+    const int C = k.tdnn1.cout, cs = k.branches[0].cout;
+    Q3_REQUIRE(k.tdnn1.cin == (i == 0 ? C0 : s.blk[i - 1].tdnn1.cout) && k.tdnn1.cin == C, Q3_ERR_UNSUPPORTED,
+               "speaker encoder: the residual connection needs equal channel counts");
+    launch_conv(k.tdnn1, x, t1.as<float>(), 1, T, 1, nullptr, nullptr, nullptr, CEPI_RELU, st);
+    // Res2Net (speaker.rs:170-189): chunk 0 passes through; branch j reads chunk j + 1 (+ the previous branch's output)
+    Q3_CHECK_CUDA(cudaMemcpyAsync(r2.p, t1.p, (size_t)cs * T * 4, cudaMemcpyDeviceToDevice, st));
+    for (int j = 0; j < (int)k.branches.size(); ++j)
+      launch_reflect_conv(k.branches[j], t1.as<float>() + (size_t)(j + 1) * cs * T, j > 0 ? r2.as<float>() + (size_t)j * cs * T : nullptr,
+                          r2.as<float>() + (size_t)(j + 1) * cs * T, k.dil, T, st);
+    launch_conv(k.tdnn2, r2.as<float>(), t2.as<float>(), 1, T, 1, nullptr, nullptr, nullptr, CEPI_RELU, st);
+    // squeeze-excitation (speaker.rs:214-221) + residual (:266), written straight into its slice of the MFA concatenation
+    spk_channel_stats_kernel<<<C, 256, 0, st>>>(t2.as<float>(), stat.as<float>(), nullptr, T);
+    Q3_COUNT_LAUNCH();
+    launch_conv(k.se1, stat.as<float>(), se_a.as<float>(), 1, 1, 1, nullptr, nullptr, nullptr, CEPI_RELU, st);
+    launch_conv(k.se2, se_a.as<float>(), se_b.as<float>(), 1, 1, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+    float* o = cat.as<float>() + cat_off;
+    spk_se_apply_kernel<<<std::min(1024, ceil_div(C * T, 256)), 256, 0, st>>>(t2.as<float>(), se_b.as<float>(), x, o, C, T);
+    Q3_COUNT_LAUNCH();
+    Q3_LAUNCH_CHECK();
+    x = o;
+    cat_off += (size_t)C * T;
+  }
+  // MFA (speaker.rs:460-464), ASP (speaker.rs:294-346), FC (:470)
+  launch_conv(s.mfa, cat.as<float>(), hm.as<float>(), 1, T, 1, nullptr, nullptr, nullptr, CEPI_RELU, st);
+  spk_channel_stats_kernel<<<Cm, 256, 0, st>>>(hm.as<float>(), stat.as<float>(), stat.as<float>() + Cm, T);
+  Q3_COUNT_LAUNCH();
+  Q3_CHECK_CUDA(cudaMemcpyAsync(attn_in.p, hm.p, (size_t)Cm * T * 4, cudaMemcpyDeviceToDevice, st));
+  spk_broadcast_stats_kernel<<<std::min(1024, ceil_div(2 * Cm * T, 256)), 256, 0, st>>>(stat.as<float>(), stat.as<float>() + Cm,
+                                                                                        attn_in.as<float>() + (size_t)Cm * T, Cm, T);
+  Q3_COUNT_LAUNCH();
+  launch_conv(s.asp_tdnn, attn_in.as<float>(), a1.as<float>(), 1, T, 1, nullptr, nullptr, nullptr, CEPI_RELU, st);
+  spk_tanh_kernel<<<std::min(1024, ceil_div(s.asp_tdnn.cout * T, 256)), 256, 0, st>>>(a1.as<float>(), (size_t)s.asp_tdnn.cout * T);
+  Q3_COUNT_LAUNCH();
+  launch_conv(s.asp_conv, a1.as<float>(), a2.as<float>(), 1, T, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  spk_asp_pool_kernel<<<Cm, 256, 0, st>>>(hm.as<float>(), a2.as<float>(), pooled.as<float>(), Cm, T);
+  Q3_COUNT_LAUNCH();
+  Q3_LAUNCH_CHECK();
+  launch_conv(s.fc, pooled.as<float>(), out, 1, 1, 1, nullptr, nullptr, nullptr, CEPI_NONE, st);
+  Q3_CHECK_CUDA(cudaStreamSynchronize(st));       // the scratch buffers above are freed on return
 }

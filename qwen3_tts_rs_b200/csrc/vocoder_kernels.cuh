@@ -40,7 +40,7 @@ __global__ void voc_codes_to_tensor_kernel(const uint32_t* __restrict__ frames, 
 }
 
 // ---- implicit-GEMM causal conv1d ----------------------------------------------------------------------
-enum ConvEpi { CEPI_NONE = 0, CEPI_GELU = 1, CEPI_CLAMP = 2 };
+enum ConvEpi { CEPI_NONE = 0, CEPI_GELU = 1, CEPI_CLAMP = 2, CEPI_RELU = 3 };   // RELU: speaker encoder TDNN blocks
 struct ConvArgs {
   const float* x;       // [B][Cin][T]
   const float* w;       // re-packed at load: [Cin*k][Cout]  (row = ci*k + j)
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(256) voc_conv1d_kernel(const ConvArgs a) {
       const size_t o = ((size_t)b * a.Cout + co) * a.T + t;
       float v = acc[i][j] + bv;
       if (a.epi == CEPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));   // erf GELU
+      if (a.epi == CEPI_RELU) v = fmaxf(v, 0.f);
       if (a.scale) v = v * sc;
       if (a.res) v = a.res[o] + v;
       if (a.epi == CEPI_CLAMP) v = fminf(fmaxf(v, -1.0f), 1.0f);

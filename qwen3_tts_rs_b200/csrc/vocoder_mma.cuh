@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256, 2) voc_conv_mma_kernel(const MmaConvArgs 
           const size_t o = ((size_t)b * a.Cout + co) * a.Tout + t;
           float v = acc[mi][nj][half * 2 + e] + bv;
           if (a.epi == CEPI_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));
+          if (a.epi == CEPI_RELU) v = fmaxf(v, 0.f);
           if (a.scale) v = v * sc;
           if (a.res) v = a.res[o] + v;
           if (a.epi == CEPI_CLAMP) v = fminf(fmaxf(v, -1.0f), 1.0f);

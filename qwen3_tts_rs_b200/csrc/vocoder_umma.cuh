@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(UC_THREADS, 2) voc_conv_umma_kernel(const MmaC
         for (int e = 0; e < 4; ++e) {
           float val = __uint_as_float(r[j0 + e]) + bv;
           if (a.epi == CEPI_GELU) val = 0.5f * val * (1.0f + erff(val * 0.70710678118654752440f));
+          if (a.epi == CEPI_RELU) val = fmaxf(val, 0.f);
           if (a.scale) val = val * sc;
           o4[e] = val;
         }

@@ -507,8 +507,8 @@ def detect_spec_from_weights(shapes: Dict[str, Sequence[int]]) -> ModelSpec:
 
 def hot_path_tensor_names(spec: ModelSpec) -> Tuple[List[str], List[str]]:
     """(names read from model.safetensors, names read from speech_tokenizer/model.safetensors).  Everything else in
-    the two files (speaker_encoder.*, encoder.* of the speech tokenizer) belongs to the voice-clone front end,
-    SURVEY.md §8(f) row 4, and is not uploaded."""
+    the two files belongs to the voice-clone front end: `speaker_encoder.*` is uploaded when present
+    (load_checkpoint), `encoder.*` of the speech tokenizer (the Mimi speech encoder) is not."""
     return ([n for n, _, _ in W.talker_tensor_specs(spec)], [n for n, _, _ in W.vocoder_tensor_specs(spec.vocoder)])
 
 
@@ -534,6 +534,7 @@ class Checkpoint:
     config: Optional[ParsedModelConfig]
     talker_weights: Dict[str, torch.Tensor]      # stored dtype (bf16 in the published checkpoints); uploaded as bf16
     vocoder_weights: Dict[str, torch.Tensor]     # uploaded as f32 ("always F32", lib.rs:344-345)
+    speaker_weights: Dict[str, torch.Tensor] = None   # speaker_encoder.* when the checkpoint has them (Base models), else {}
 
 
 def load_checkpoint(model_dir: str) -> Checkpoint:
@@ -560,7 +561,10 @@ def load_checkpoint(model_dir: str) -> Checkpoint:
     vmissing = [n for n in vnames if n not in vhdr]
     if vmissing:
         raise KeyError(f"Missing weight: {vmissing[0]} (and {len(vmissing) - 1} more) in {st_path}")
-    return Checkpoint(spec, cfg, load_safetensors(model_path, tnames), load_safetensors(st_path, vnames))
+    # try_load_speaker_encoder (lib.rs:1333-1360): present only in checkpoints that carry `speaker_encoder.*` keys
+    snames = sorted(n for n in hdr if n.startswith("speaker_encoder."))
+    return Checkpoint(spec, cfg, load_safetensors(model_path, tnames), load_safetensors(st_path, vnames),
+                      load_safetensors(model_path, snames) if snames else {})
 
 
 def export_checkpoint(model_dir: str, spec: ModelSpec, talker_weights: Dict[str, torch.Tensor],

@@ -29,7 +29,7 @@ EXPORTS = [
     "q3_session_create", "q3_session_reset", "q3_session_destroy", "q3_session_stream", "q3_session_synchronize",
     "q3_prefill_embeds", "q3_prefill_ids", "q3_prefill_voice_clone", "q3_set_trailing_text", "q3_set_trailing_ids",
     "q3_generate", "q3_generate_async", "q3_get_codes", "q3_stream_next", "q3_session_set_stream_context",
-    "q3_vocoder_decode", "q3_vocode_session",
+    "q3_vocoder_decode", "q3_vocode_session", "q3_speaker_encode", "q3_speaker_embed_dim",
     "q3_talker_step", "q3_code_predictor_frame", "q3_sample",
     "q3_fused_residual_rmsnorm", "q3_fused_residual_rmsnorm_host", "q3_session_timing",
 ]
@@ -119,6 +119,9 @@ def load() -> C.CDLL:
     lib.q3_prefill_embeds.argtypes = [vp, vp, vp, i32]
     lib.q3_prefill_ids.argtypes = [vp, vp, vp, vp, i32]
     lib.q3_prefill_voice_clone.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32]
+    lib.q3_speaker_encode.argtypes = [vp, vp, i32, i32, vp]
+    lib.q3_speaker_embed_dim.argtypes = [vp]
+    lib.q3_speaker_embed_dim.restype = i32
     lib.q3_set_trailing_text.argtypes = [vp, vp, vp, i32, vp]
     lib.q3_set_trailing_ids.argtypes = [vp, vp, vp, i32, i32, i32]
     lib.q3_generate.argtypes = [vp, i32, vp, vp]

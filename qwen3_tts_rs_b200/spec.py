@@ -72,6 +72,23 @@ class VocoderSpec:
 
 
 @dataclass(frozen=True)
+class SpeakerSpec:
+    """SpeakerEncoderConfig (config.rs:102-175): ECAPA-TDNN on a 128-band mel spectrogram."""
+    mel_dim: int = 128
+    enc_dim: int = 1024
+    enc_channels: Tuple[int, ...] = (512, 512, 512, 512, 1536)     # initial, 3 x SE-Res2Net, MFA
+    enc_kernel_sizes: Tuple[int, ...] = (5, 3, 3, 3, 1)
+    enc_dilations: Tuple[int, ...] = (1, 2, 3, 4, 1)
+    enc_attention_channels: int = 128
+    enc_res2net_scale: int = 8
+    enc_se_channels: int = 128
+
+
+TINY_SPEAKER = SpeakerSpec(mel_dim=32, enc_dim=256, enc_channels=(64, 64, 64, 64, 192), enc_attention_channels=32,
+                           enc_res2net_scale=4, enc_se_channels=32)
+
+
+@dataclass(frozen=True)
 class ModelSpec:
     name: str
     # talker (talker.rs:208-274)

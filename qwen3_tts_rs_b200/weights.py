@@ -207,6 +207,33 @@ def make_talker_weights(spec: ModelSpec, base_seed: int = BASE_SEED,
     return out
 
 
+def speaker_tensor_specs(c) -> Iterator[Tuple[str, tuple, str]]:
+    """Names from speaker.rs:362-434 (prefix speaker_encoder.*)."""
+    p = "speaker_encoder"
+    ch, ks = c.enc_channels, c.enc_kernel_sizes
+    def conv(name, cout, cin, k):
+        yield f"{p}.{name}.weight", (cout, cin, k), "conv"
+        yield f"{p}.{name}.bias", (cout,), "bias"
+    yield from conv("blocks.0.conv", ch[0], c.mel_dim, ks[0])
+    for i in range(1, 4):
+        C, cs = ch[i], ch[i] // c.enc_res2net_scale
+        yield from conv(f"blocks.{i}.tdnn1.conv", C, C, 1)
+        for j in range(c.enc_res2net_scale - 1):
+            yield from conv(f"blocks.{i}.res2net_block.blocks.{j}.conv", cs, cs, ks[i])
+        yield from conv(f"blocks.{i}.tdnn2.conv", C, C, 1)
+        yield from conv(f"blocks.{i}.se_block.conv1", c.enc_se_channels, C, 1)
+        yield from conv(f"blocks.{i}.se_block.conv2", C, c.enc_se_channels, 1)
+    yield from conv("mfa.conv", ch[4], sum(ch[1:4]), ks[4])
+    yield from conv("asp.tdnn.conv", c.enc_attention_channels, ch[4] * 3, 1)
+    yield from conv("asp.conv", ch[4], c.enc_attention_channels, 1)
+    yield from conv("fc", c.enc_dim, ch[4] * 2, 1)
+
+
+def make_speaker_weights(c, base_seed: int = BASE_SEED) -> Dict[str, torch.Tensor]:
+    """All speaker-encoder tensors, F32."""
+    return {name: make_tensor(name, shape, kind, base_seed) for name, shape, kind in speaker_tensor_specs(c)}
+
+
 def make_vocoder_weights(v: VocoderSpec, base_seed: int = BASE_SEED) -> Dict[str, torch.Tensor]:
     """All vocoder tensors, F32 (the vocoder is F32 on every device, src/lib.rs:344-345)."""
     return {name: make_tensor(name, shape, kind, base_seed)

@@ -126,6 +126,8 @@ extern "C" {
 
     pub fn q3_prefill_embeds(s: *mut q3_session, embeds: *const u16, lens: *const i32, l_max: i32) -> c_int;
     pub fn q3_prefill_ids(s: *mut q3_session, text_ids: *const i32, codec_ids: *const i32, lens: *const i32, l_max: i32) -> c_int;
+    pub fn q3_speaker_embed_dim(m: *const q3_model) -> i32;
+    pub fn q3_speaker_encode(m: *const q3_model, mel: *const f32, batch: i32, t: i32, embed_out: *mut f32) -> c_int;
     pub fn q3_prefill_voice_clone(s: *mut q3_session, text_ids: *const i32, codec_ids: *const i32, lens: *const i32, l_max: i32,
                                   speaker_embeds: *const u16, ref_codes: *const u32, t_ref: *const i32, t_ref_max: i32) -> c_int;
     pub fn q3_set_trailing_text(s: *mut q3_session, trailing: *const u16, lt: *const i32, lt_max: i32, tts_pad: *const u16) -> c_int;
