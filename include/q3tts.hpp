@@ -1103,6 +1103,16 @@ class Qwen3TTS {
     audio.samples.erase(audio.samples.begin(), audio.samples.begin() + std::min(cut, audio.samples.size()));
     return audio;
   }
+  /* ref: SpeakerEncoder::forward, src/models/speaker.rs:448-476 (has_speaker_encoder: lib.rs:389-391).  mel: f32 [mel_dim][t] of one
+     utterance (the mel front end, src/audio/mel.rs, is the caller's) -> the VoiceClonePrompt's speaker embedding. */
+  bool supports_voice_cloning() const { return q3_speaker_embed_dim(model_->handle()) > 0; }
+  std::vector<float> speaker_encode(const std::vector<float>& mel, int32_t t) const {
+    const int32_t dim = q3_speaker_embed_dim(model_->handle());
+    if (dim <= 0) throw Error(Q3_ERR_STATE, "model has no speaker-encoder weights (speaker_encoder.*)");
+    std::vector<float> out((size_t)dim);
+    check(q3_speaker_encode(model_->handle(), mel.data(), 1, t, out.data()));
+    return out;
+  }
   /* ref: decode_codes, lib.rs:881-890. */
   AudioBuffer decode_codes(const FrameCodes& codes) const {
     const std::vector<int64_t> t = codes_to_tensor(codes);
