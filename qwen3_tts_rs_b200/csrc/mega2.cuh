@@ -98,6 +98,11 @@ struct M2Args {
 // (ld.relaxed.gpu -> LDG.E.STRONG.GPU) is served at the line's home L2 partition on this two-die part and measured
 // 2-3x slower for the all-CTAs-read-the-same-lines pattern of the activation vectors; the tag makes a stale or
 // torn-between-slots read harmless (it is simply repeated), and each 64-bit slot is written by ONE 64-bit store.
+// HARDWARE-SPECIFIC ASSUMPTION: under the PTX memory model a weak load racing with another CTA's store is a data race;
+// what this relies on is that sm_100 performs an aligned 8-byte (and each half of a 16-byte) global access as a single
+// copy, so a reader sees a slot's {payload, tag} pair entirely old or entirely new.  -DM2_STRONG_LOADS builds the
+// model-conformant variant (ld.relaxed.gpu); the repeat test of tests/test_gpu_parity.py (150 identical frames, bit-equal
+// logits) and the per-frame follow-mode comparison are the stress tests of the default.
 #ifndef M2_STRONG_LOADS
 __device__ __forceinline__ void ld_slot2(const void* p, u64& a, u64& b) {
   asm volatile("ld.global.cg.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p));
