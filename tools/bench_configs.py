@@ -65,3 +65,22 @@ line("configs[3] stateful streaming, chunk 2 frames (exact PCM)", n // 1920, dt,
 for b in (4, 32):
     nf, dt = run_batch(tts, prompts[:b], 128)
     line(f"configs[4] 1.7B CustomVoice, {b} utterances on this GPU (8-GPU share = 4)", nf, dt)
+# SURVEY 8(f) row 4 (not a BASELINE configuration): the voice-clone front end on the 0.6B Base dimensions (speaker embedding
+# width = talker hidden = 1024): ECAPA speaker encoder on a 3 s mel spectrogram (24 kHz, hop 256 -> 282 frames), then an ICL
+# voice-clone request (60 reference frames + transcript) through synthesize_voice_clone
+del tts
+w = dict(W.make_talker_weights(spec06)); vw = dict(W.make_vocoder_weights(spec06.vocoder)); vw.update(W.make_speaker_weights(S.SpeakerSpec()))
+tts = api.Qwen3TTS.from_weights(spec06, w, vw)
+mel = (np.random.default_rng(0).standard_normal((1, 128, 282)) * 2 - 3).astype(np.float32)
+tts.speaker_encode(mel)
+t0 = time.perf_counter()
+for _ in range(5): emb = tts.speaker_encode(mel)
+print(f"{'f4 speaker encoder (ECAPA-TDNN), 3 s of audio (282 mel frames)':62s} wall {(time.perf_counter() - t0) / 5 * 1e3:9.2f} ms per utterance", flush=True)
+ref = np.random.default_rng(1).integers(0, 2048, size=(60, 16)).astype(np.uint32)
+vc = api.VoiceClonePrompt(emb[0], ref, ids(9, 20, spec06))
+o = api.SynthesisOptions(max_length=128, eos_token_id=None)
+tts.synthesize_voice_clone([ids(44, 30, spec06)], [vc], options=o, seeds=[42])
+t0 = time.perf_counter()
+for _ in range(3): audio = tts.synthesize_voice_clone([ids(44, 30, spec06)], [vc], options=o, seeds=[42])
+dt = (time.perf_counter() - t0) / 3
+line("f4 0.6B voice clone (ICL: 60 reference frames), batch 1", len(audio[0].samples) // 1920, dt)
