@@ -173,3 +173,31 @@ def test_synthesize_voice_clone_budget_and_cut_rule():
     assert all(len(a) == 6 * 1920 for a in audio)
     with pytest.raises(ValueError):
         tts.generate_codes_voice_clone(texts, [icl[0], xv[0]], options=opts)
+
+
+def test_concurrent_sessions_on_one_model_from_threads():
+    """a finalized model is read-only and shareable across threads, one session per request.  Three threads
+    synthesize different utterances at the same time on one model (ctypes drops the GIL inside the C ABI, so the persistent
+    cooperative kernels, the vocoder kernels and the session pools of the three requests really interleave); every result must
+    equal the same request run alone, bit for bit."""
+    import threading
+    spec = S.SPEC_TINY
+    tts = gpu_tts(spec, with_vocoder=True, vkey="tiny")
+    reqs = [([W.synthetic_prompt(3 * i + j, spec) for j in range(1 + i)], [100 + 3 * i + j for j in range(1 + i)]) for i in range(3)]
+    opts = api.SynthesisOptions(max_length=24)
+    alone = [tts.synthesize_with_voice(p, options=opts, seeds=s) for p, s in reqs]
+    for rounds in range(3):
+        out, errs = [None] * 3, []
+        def work(i):
+            try:
+                out[i] = tts.synthesize_with_voice(reqs[i][0], options=opts, seeds=reqs[i][1])
+            except Exception as e:      # noqa: BLE001 -- reported below
+                errs.append((i, repr(e)))
+        th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+        for t in th: t.start()
+        for t in th: t.join()
+        assert not errs, errs
+        for i in range(3):
+            assert len(out[i]) == len(alone[i])
+            for a, b in zip(out[i], alone[i]):
+                assert np.array_equal(a.samples, b.samples), ("request differs when run concurrently", i, rounds)
