@@ -176,6 +176,11 @@ q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_
  *   left_context_frames  = c > 0: re-decode form -- the previous min(c, frames so far) frames are decoded again in front of
  *     the chunk and their samples dropped; approximate for finite c (the pre-transformer sees only c frames of history). */
 q3_status q3_session_set_stream_context(q3_session* s, int32_t left_context_frames);
+/* Extension (no reference counterpart; StreamingSession::next_chunk always emits chunk_frames, src/lib.rs:1650-1759): the FIRST
+ * q3_stream_next of the session generates only min(first_chunk_frames, chunk_frames) frames, later ones chunk_frames -- with the
+ * stateful form above the waveform does not depend on where the chunks are cut, so a 2-frame first chunk gives the time to first
+ * audio of 2-frame chunks at the throughput of 10-frame chunks.  0 (default) = every chunk has chunk_frames. */
+q3_status q3_session_set_first_chunk(q3_session* s, int32_t first_chunk_frames);
 
 /* ref: Decoder12Hz::decode (src/models/codec/decoder_12hz.rs:411-505).  codes: i64 [B][16][T]
  * (host, the codes_to_tensor layout of src/lib.rs:1417-1431); pcm: f32 [B][T*1920] (host). */

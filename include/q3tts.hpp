@@ -109,6 +109,8 @@ struct SynthesisOptions {
   /* not in the reference (opt-in, see q3_session_set_stream_context): 0 = the reference's stateless chunks, < 0 = stateful
      streaming (carried vocoder state, streamed PCM == non-streamed PCM), c > 0 = c left-context frames decoded again */
   int32_t stream_left_context = 0;
+  /* not in the reference (opt-in, see q3_session_set_first_chunk): frames of the first streamed chunk, 0 = chunk_frames */
+  int32_t stream_first_chunk = 0;
 
   q3_gen_config to_gen_config() const {
     q3_gen_config g{};
@@ -797,6 +799,10 @@ class Session {
     check(q3_session_create(m.handle(), batch, max_seq, &g, seeds.data(), &h_));
     if (o.stream_left_context != 0) {
       const q3_status st = q3_session_set_stream_context(h_, o.stream_left_context);
+      if (st != Q3_OK) { q3_session_destroy(h_); h_ = nullptr; check(st); }
+    }
+    if (o.stream_first_chunk != 0) {
+      const q3_status st = q3_session_set_first_chunk(h_, o.stream_first_chunk);
       if (st != Q3_OK) { q3_session_destroy(h_); h_ = nullptr; check(st); }
     }
   }

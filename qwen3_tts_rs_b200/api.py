@@ -50,6 +50,10 @@ class SynthesisOptions:
     # session carries the vocoder's cross-chunk state: streamed PCM == non-streamed PCM at a per-chunk cost independent of the
     # utterance length); c > 0 = c frames of left context decoded again in front of every streamed chunk and dropped.
     stream_left_context: int = 0
+    # Not in the reference (opt-in): frames of the FIRST streamed chunk (0 = chunk_frames).  With stream_left_context = -1 the
+    # waveform does not depend on where chunks are cut, so first chunk 2 + chunk_frames 10 = TTFA of 2-frame chunks at the
+    # throughput of 10-frame chunks.
+    stream_first_chunk: int = 0
 
     def to_gen_config(self) -> L.GenConfig:
         g = L.GenConfig()
@@ -210,6 +214,8 @@ class Session:
         L.check(self.lib.q3_session_create(model.handle, batch, self.max_seq, C.byref(self.cfg), sd, C.byref(self.handle)))
         if options.stream_left_context:
             L.check(self.lib.q3_session_set_stream_context(self.handle, int(options.stream_left_context)))
+        if options.stream_first_chunk:
+            L.check(self.lib.q3_session_set_first_chunk(self.handle, int(options.stream_first_chunk)))
 
     def reset(self, seeds: Sequence[int]):
         sd = (C.c_uint64 * self.B)(*[int(s) & ((1 << 64) - 1) for s in seeds])

@@ -69,6 +69,7 @@ struct q3_session {
   bool use_mega = false;
   int mega_ver = 2;                // 1: fence-based grid barriers (mega.cuh), 2: tagged dataflow phases (mega2.cuh)
   DBuf tr_ids, tr_proj;            // staging of q3_set_trailing_ids
+  int stream_first = 0;            // q3_session_set_first_chunk: frames of the first streamed chunk (0 = chunk_frames)
   DBuf pf_tid, pf_cid;             // staging of q3_prefill_ids
   DBuf pf_spk, pf_ref;             // q3_prefill_voice_clone: speaker embeddings, reference codes
   DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag;
@@ -1586,6 +1587,13 @@ q3_status q3_session_set_stream_context(q3_session* s, int32_t left_context_fram
   Q3_API_END
 }
 
+q3_status q3_session_set_first_chunk(q3_session* s, int32_t first_chunk_frames) {
+  Q3_API_BEGIN
+  Q3_REQUIRE(s && first_chunk_frames >= 0, Q3_ERR_INVALID, "bad argument");
+  s->stream_first = first_chunk_frames;
+  Q3_API_END
+}
+
 q3_status q3_vocode_session(q3_session* s, int32_t max_frames, float* pcm) {
   Q3_API_BEGIN
   Q3_REQUIRE(s && max_frames >= 0, Q3_ERR_INVALID, "bad argument");
@@ -1613,7 +1621,9 @@ q3_status q3_stream_next(q3_session* s, uint32_t* codes, float* pcm, int32_t* n_
   Q3_CHECK_CUDA(cudaSetDevice(s->m->d.device));
   const int B = s->B, chunk = std::max(1, s->cfg.chunk_frames), up = vocoder_total_upsample(s->m);
   sample_first_if_needed(s);
-  run_frames(s, frames_budget(s, chunk));
+  // opt-in (q3_session_set_first_chunk): the first chunk of the stream is shorter, for a low time to first audio
+  const int gen = (s->stream_first > 0 && s->frames_run == 0) ? std::min(chunk, s->stream_first) : chunk;
+  run_frames(s, frames_budget(s, gen));
   std::vector<int> nf(B), dn(B);
   Q3_CHECK_CUDA(cudaMemcpyAsync(nf.data(), s->n_frames.p, B * 4, cudaMemcpyDeviceToHost, s->st));
   Q3_CHECK_CUDA(cudaMemcpyAsync(dn.data(), s->done.p, B * 4, cudaMemcpyDeviceToHost, s->st));

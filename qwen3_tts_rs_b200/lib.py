@@ -28,7 +28,7 @@ EXPORTS = [
     "q3_model_create", "q3_model_set_tensor", "q3_model_finalize", "q3_model_destroy",
     "q3_session_create", "q3_session_reset", "q3_session_destroy", "q3_session_stream", "q3_session_synchronize",
     "q3_prefill_embeds", "q3_prefill_ids", "q3_prefill_voice_clone", "q3_set_trailing_text", "q3_set_trailing_ids",
-    "q3_generate", "q3_generate_async", "q3_get_codes", "q3_stream_next", "q3_session_set_stream_context",
+    "q3_generate", "q3_generate_async", "q3_get_codes", "q3_stream_next", "q3_session_set_stream_context", "q3_session_set_first_chunk",
     "q3_vocoder_decode", "q3_vocode_session", "q3_speaker_encode", "q3_speaker_embed_dim",
     "q3_talker_step", "q3_code_predictor_frame", "q3_sample",
     "q3_fused_residual_rmsnorm", "q3_fused_residual_rmsnorm_host", "q3_session_timing",
@@ -137,6 +137,7 @@ def load() -> C.CDLL:
     lib.q3_fused_residual_rmsnorm_host.argtypes = [vp, vp, vp, vp, vp, i32, i32, C.c_float, C.c_int, i32]
     lib.q3_session_timing.argtypes = [vp, C.POINTER(Timing)]
     lib.q3_session_set_stream_context.argtypes = [vp, i32]
+    lib.q3_session_set_first_chunk.argtypes = [vp, i32]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("q3_last_error", "q3_abi_version", "q3_kernel_launch_count", "q3_model_destroy",

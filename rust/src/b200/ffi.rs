@@ -122,6 +122,7 @@ extern "C" {
     pub fn q3_session_stream(s: *mut q3_session) -> *mut c_void;
     pub fn q3_session_synchronize(s: *mut q3_session) -> c_int;
     pub fn q3_session_set_stream_context(s: *mut q3_session, left_context_frames: i32) -> c_int;
+    pub fn q3_session_set_first_chunk(s: *mut q3_session, first_chunk_frames: i32) -> c_int;
     pub fn q3_session_timing(s: *mut q3_session, out: *mut q3_timing) -> c_int;
 
     pub fn q3_prefill_embeds(s: *mut q3_session, embeds: *const u16, lens: *const i32, l_max: i32) -> c_int;

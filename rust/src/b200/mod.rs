@@ -352,6 +352,11 @@ impl<'a> B200Session<'a> {
         ffi::check(unsafe { ffi::q3_session_set_stream_context(self.raw, frames) })
     }
 
+    /// Opt-in: the first streamed chunk has only `frames` frames (low time to first audio), later ones `chunk_frames`.
+    pub fn set_first_chunk(&mut self, frames: i32) -> Result<()> {
+        ffi::check(unsafe { ffi::q3_session_set_first_chunk(self.raw, frames) })
+    }
+
     pub fn frames_generated(&self) -> usize {
         self.frames_generated
     }

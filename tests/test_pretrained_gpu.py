@@ -98,6 +98,24 @@ def test_stateful_streaming_equals_the_non_streamed_waveform(chunk):
         assert float(np.sqrt(np.mean((got - ref) ** 2))) <= 1e-3
 
 
+def test_short_first_chunk_keeps_the_stateful_stream_exact():
+    """q3_session_set_first_chunk (extension): first chunk 2 frames, then chunks of 10 -- the chunk sizes are 2, 10, 10, 10, 8,
+    the codes are those of the non-streamed run and, in stateful mode, so is the waveform (<= 1e-6)."""
+    spec = S.SPEC_TINY
+    tts = api.Qwen3TTS.from_weights(spec, talker_weights(spec), vocoder_weights(spec.vocoder, spec.name))
+    ids = W.synthetic_prompt(2, spec)
+    F = 40
+    whole = tts.synthesize_with_voice([ids], options=api.SynthesisOptions(max_length=F), seeds=[99])[0]
+    opts = api.SynthesisOptions(max_length=F, chunk_frames=10, stream_left_context=-1, stream_first_chunk=2, seed=99)
+    sizes, pcm = [], []
+    for chunk in tts.synthesize_streaming(ids, options=opts):
+        sizes.append(len(chunk.samples) // 1920)
+        pcm.append(chunk.samples)
+    assert sizes == [2, 10, 10, 10, 8]
+    got = np.concatenate(pcm)
+    assert got.shape == whole.samples.shape and np.abs(got - whole.samples).max() <= 1e-6
+
+
 def test_cuda_path_against_the_committed_golden_vectors():
     """tests/golden/tiny_model_fixture.json (frozen oracle outputs): the vocoder's PCM for the fixture codes within the
     1e-3 RMS bar, sample for sample on the frozen subsets, and the first semantic token of the fixture utterance (it

@@ -62,6 +62,17 @@ for rep in range(3):
         n += len(chunk.samples)
     dt = time.perf_counter() - t0
 line("configs[3] stateful streaming, chunk 2 frames (exact PCM)", n // 1920, dt, f" TTFA {first*1e3:.1f} ms")
+# stateful, first chunk 2 frames then chunks of 10 (q3_session_set_first_chunk): the TTFA of the 2-frame stream at the throughput of 10-frame chunks
+opts3 = api.SynthesisOptions(max_length=120, seed=42, chunk_frames=10, stream_left_context=-1, stream_first_chunk=2)
+for rep in range(3):
+    t0 = time.perf_counter()
+    st = tts.synthesize_voice_design_streaming(text, instr, options=opts3)
+    first = None; n = 0
+    for chunk in st:
+        if first is None: first = time.perf_counter() - t0
+        n += len(chunk.samples)
+    dt = time.perf_counter() - t0
+line("configs[3] stateful streaming, first chunk 2 then 10 frames", n // 1920, dt, f" TTFA {first*1e3:.1f} ms")
 for b in (4, 32):
     nf, dt = run_batch(tts, prompts[:b], 128)
     line(f"configs[4] 1.7B CustomVoice, {b} utterances on this GPU (8-GPU share = 4)", nf, dt)
