@@ -90,6 +90,8 @@ struct M2Args {
   int pf_sleep;         // ring kernel: nanoseconds the producer warp sleeps between polls of a full ring
   int m4_slots;         // mega4.cuh: ring slots in use
   int m4_red2;          // mega4.cuh: the combine buffer is double-buffered over tiles
+  u64* xchg;            // m2_attn_units: exchange slots of the splits of a long row, [rows x kv_heads x M2_SPLIT_NS][M2_XCHG_SLOTS]
+  int split_min_l;      // > 0: talker attention of this launch runs m2_attn_units, rows with >= split_min_l positions are split
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -934,8 +936,11 @@ constexpr int M2_ATT_FAST_L = 16;
 #ifndef M2_ATT_U
 #define M2_ATT_U 16
 #endif
+__device__ __noinline__ unsigned long long m2_attn_units(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
+                                                         const uint32_t tag);
 __device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
                                                    const uint32_t tag) {
+  if (a.split_min_l > 0 && !(p.flags & PF_CP) && p.S == 1) return m2_attn_units(a, p, smem, gs, tag);
   const bool cp = (p.flags & PF_CP) != 0;
   const bool prof_on = M2_PROF_ENABLED && a.prof != nullptr;
   const int max_seq = cp ? a.cp_max_seq : a.max_seq;
@@ -1182,6 +1187,322 @@ __device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phas
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Split-KV form of the talker's decode attention (one token per row), used for the launches in which some row's context can
+// reach a.split_min_l positions (host decision, q3tts.cu mega2_launch).  A row whose context is shorter takes exactly the
+// code path of m2_attn (same row order per warp, same reduction trees: bit-identical results); a longer row is cut into
+// M2_SPLIT_NS ranges of cache rows handled by M2_SPLIT_NS CTAs, which exchange the softmax maximum, the normaliser and
+// their partial P*V sums through tagged slots in global memory (a.xchg).  Whether a row is split depends on ITS context
+// length only, never on the other rows of the batch, so a row of a batch still equals its batch-1 run bit for bit.
+// At 2000 positions m2_attn is bound by the latency of its batches of cache rows on the 8 x B CTAs that have work
+// (~40 us per layer); here up to 4 x 8 x B CTAs share them.  The current position's K / V rows are appended by the last
+// split only; every other cache row was written at least one frame (549 phases, several of them release / acquire
+// barriers) earlier, by whichever CTA owned the position then.
+constexpr int M2_SPLIT_NS = 4;
+constexpr int M2_XCHG_SLOTS = 4 + 256;          // per split: max[2], sum[2], partial P*V [2][128]
+__device__ __noinline__ unsigned long long m2_attn_units(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
+                                                         const uint32_t tag) {
+  const bool cp = (p.flags & PF_CP) != 0;
+  const bool prof_on = M2_PROF_ENABLED && a.prof != nullptr;
+  const int max_seq = cp ? a.cp_max_seq : a.max_seq;
+  const bf16* cos_tab = cp ? a.cp_cos : a.t_cos;
+  const bf16* sin_tab = cp ? a.cp_sin : a.t_sin;
+  const int* pos_base = cp ? nullptr : a.fs.offset;
+  const int heads = p.N, kv_heads = p.K, S = p.S, nh = heads + 2 * kv_heads;
+  const int sc_n = (max_seq + 3) & ~3;                   // keeps everything behind the score arrays 16-byte aligned
+  float* sc0 = reinterpret_cast<float*>(smem);          // [max_seq]
+  float* sc1 = sc0 + sc_n;
+  float* qs = sc1 + sc_n;                                // [2][128] rotated queries (bf16 values)
+  float* red = qs + 256;                                 // [16][2][128]
+  bf16* Ks = reinterpret_cast<bf16*>(red + 16 * 2 * 128);   // [16][128] fast path: K rows (row pos = this token)
+  bf16* Vs = Ks + M2_ATT_FAST_L * 128;                        // [16][128]
+  bf16* kcur = Vs + M2_ATT_FAST_L * 128;                      // [128] general path: this token's rotated K row
+  bf16* vcur = kcur + 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t xtag = tag - 1u;
+  const float scale = rbf(0.08838834764831845f);
+  const int n_rows = p.T;                           // S == 1: one token per row
+  int* s_L = reinterpret_cast<int*>(vcur + 128);     // [16] context length of every row of the phase
+  int* s_ub = s_L + 16;                              // [17] first work unit of every row
+  m2_wait(gs, p.flags);
+  if (prof_on) prof2(a, 6);
+  if (prof_on) m2_stamp(gs, 0);
+  if (tid < n_rows) s_L[tid] = __ldcg(pos_base + tid) + p.pos_add + 1;
+  m2_csync();
+  if (tid == 0) {
+    int u = 0;
+    for (int r = 0; r < n_rows; ++r) { s_ub[r] = u; u += kv_heads * (s_L[r] >= a.split_min_l ? M2_SPLIT_NS : 1); }
+    s_ub[n_rows] = u;
+  }
+  m2_csync();
+  const int n_units = s_ub[n_rows];
+  for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+    int b = 0;
+    while (b + 1 < n_rows && s_ub[b + 1] <= unit) ++b;
+    const int L = s_L[b], pos = L - 1;
+    const int ns = L >= a.split_min_l ? M2_SPLIT_NS : 1;
+    const int ru = unit - s_ub[b], kvh = ru / ns, split = ru - kvh * ns;
+    bf16* kbase = const_cast<bf16*>(p.W) + ((size_t)b * kv_heads + kvh) * max_seq * 128;
+    bf16* vbase = const_cast<bf16*>(p.W2) + ((size_t)b * kv_heads + kvh) * max_seq * 128;
+    // rows [j_lo, j_hi) of the cache belong to this split; the last split owns the current position (it appends K / V)
+    const int chunk = (L + ns - 1) / ns;
+    const int j_lo = split * chunk, j_hi = min(L, j_lo + chunk);
+    const bool owner = split == ns - 1;
+    u64* xg = a.xchg + (size_t)(unit - split) * M2_XCHG_SLOTS;      // exchange slots of the item's splits: [ns][M2_XCHG_SLOTS]
+    {
+      const int s = 0;
+      const int t = b;
+      const bool fast = L <= M2_ATT_FAST_L;      // (ns == 1 there: split_min_l > 16)
+      uint2 kpre = make_uint2(0u, 0u), vpre = make_uint2(0u, 0u);
+      if (fast) {
+        // warps 4..15: rows j < pos of K and V -> shared memory (16 lanes x 16 B per row)
+        if (warp >= 4) {
+          for (int i = tid - 128; i < 2 * pos * 16; i += MEGA_THREADS - 128) {
+            const int r = i >> 4, c16 = i & 15;
+            const bool isv = r >= pos;
+            const int j = isv ? r - pos : r;
+            const uint4 v = ldcg16((isv ? vbase : kbase) + (size_t)j * 128 + c16 * 8);
+            *reinterpret_cast<uint4*>((isv ? Vs : Ks) + j * 128 + c16 * 8) = v;
+          }
+        }
+      } else if (ns == 1 && warp < pos) {
+        kpre = __ldcg(reinterpret_cast<const uint2*>(kbase + (size_t)warp * 128 + 4 * lane));
+        vpre = __ldcg(reinterpret_cast<const uint2*>(vbase + (size_t)warp * 128 + 4 * lane));
+      }
+      // warps 0,1: q heads 2kvh, 2kvh+1; warp 2: k; warp 3: v.  Lane l holds elements 2l, 2l+1, 64+2l, 65+2l.
+      if (warp < 2 || (warp < 4 && owner)) {
+        const int hh = warp < 2 ? 2 * kvh + warp : (warp == 2 ? heads + kvh : heads + kv_heads + kvh);
+        const u64* src = reinterpret_cast<const u64*>(p.X) + (((size_t)t * nh + hh) * 128 >> 1);
+        u64 s0, s1;
+        unsigned tries = 0;
+        for (;;) {
+          s0 = ld_slot(src + lane);
+          s1 = ld_slot(src + 32 + lane);
+          const uint32_t bad = (slot_tag(s0) ^ xtag) | (slot_tag(s1) ^ xtag);
+          if (!__any_sync(0xffffffffu, bad != 0)) break;
+          if (M2_PROF_ENABLED && gs.retries != nullptr && (threadIdx.x & 31) == 0) atomicAdd(gs.retries, 1u);
+      if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 6000000 + (int)gs.epoch); break; }
+        }
+        float v[4] = {bf_lo(slot_val(s0)), bf_hi(slot_val(s0)), bf_lo(slot_val(s1)), bf_hi(slot_val(s1))};
+        const int d0 = 2 * lane;           // v[0],v[1] -> d0, d0+1 ; v[2],v[3] -> 64+d0, 65+d0
+        if (warp == 3) {
+          bf16* dst = fast ? Vs + pos * 128 : vcur;
+          const uint32_t lo = slot_val(s0), hi = slot_val(s1);
+          *reinterpret_cast<uint32_t*>(vbase + (size_t)pos * 128 + d0) = lo;
+          *reinterpret_cast<uint32_t*>(vbase + (size_t)pos * 128 + 64 + d0) = hi;
+          *reinterpret_cast<uint32_t*>(dst + d0) = lo;
+          *reinterpret_cast<uint32_t*>(dst + 64 + d0) = hi;
+        } else {
+          const bf16* nw = warp < 2 ? p.aux : p.aux2;
+          float tmp = 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) tmp = fmaf(v[i], v[i], tmp);
+          tmp = warp_sum_xor(tmp);
+          const float sc = ref_mean_rsqrt(tmp, 128, a.eps);
+          const uint32_t w0 = *reinterpret_cast<const uint32_t*>(nw + d0), w1 = *reinterpret_cast<const uint32_t*>(nw + 64 + d0);
+          const float n0 = rbf((sc * v[0]) * bf_lo(w0)), n1 = rbf((sc * v[1]) * bf_hi(w0));
+          const float n2 = rbf((sc * v[2]) * bf_lo(w1)), n3 = rbf((sc * v[3]) * bf_hi(w1));
+          const uint32_t cw = *reinterpret_cast<const uint32_t*>(cos_tab + (size_t)pos * 64 + d0);
+          const uint32_t sw = *reinterpret_cast<const uint32_t*>(sin_tab + (size_t)pos * 64 + d0);
+          const float c0 = bf_lo(cw), c1 = bf_hi(cw), sn0 = bf_lo(sw), sn1 = bf_hi(sw);
+          const float o0 = rbf(rbf(n0 * c0) - rbf(n2 * sn0)), o1 = rbf(rbf(n1 * c1) - rbf(n3 * sn1));
+          const float o2 = rbf(rbf(n2 * c0) + rbf(n0 * sn0)), o3 = rbf(rbf(n3 * c1) + rbf(n1 * sn1));
+          if (warp < 2) {
+            *reinterpret_cast<float2*>(qs + warp * 128 + d0) = make_float2(o0, o1);
+            *reinterpret_cast<float2*>(qs + warp * 128 + 64 + d0) = make_float2(o2, o3);
+          } else {
+            bf16* dst = fast ? Ks + pos * 128 : kcur;
+            const uint32_t lo = pack2(o0, o1), hi = pack2(o2, o3);
+            *reinterpret_cast<uint32_t*>(kbase + (size_t)pos * 128 + d0) = lo;
+            *reinterpret_cast<uint32_t*>(kbase + (size_t)pos * 128 + 64 + d0) = hi;
+            *reinterpret_cast<uint32_t*>(dst + d0) = lo;
+            *reinterpret_cast<uint32_t*>(dst + 64 + d0) = hi;
+          }
+        }
+      }
+      m2_csync();      // q, this token's k/v (and, fast path, all earlier rows) in smem
+      float q0[4], q1[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { q0[i] = qs[4 * lane + i]; q1[i] = qs[128 + 4 * lane + i]; }
+      if (fast) {
+        // one position per warp; both heads
+        if (warp < L) {
+          const uint2 u = *reinterpret_cast<const uint2*>(Ks + warp * 128 + 4 * lane);
+          const float k0 = bf_lo(u.x), k1 = bf_hi(u.x), k2 = bf_lo(u.y), k3 = bf_hi(u.y);
+          float d0 = q0[0] * k0 + q0[1] * k1 + q0[2] * k2 + q0[3] * k3;
+          float d1 = q1[0] * k0 + q1[1] * k1 + q1[2] * k2 + q1[3] * k3;
+          d0 = warp_sum_xor(d0);
+          d1 = warp_sum_xor(d1);
+          if (lane == 0) {
+            sc0[warp] = rbf(rbf(d0) * scale);
+            sc1[warp] = rbf(rbf(d1) * scale);
+          }
+        }
+        m2_csync();
+        // softmax of the (<= 16) scores of head h by warp h, one position per lane; probabilities (rounded to bf16 as the
+        // reference's softmax output is) go back into the score array
+        if (warp < 2) {
+          float* sc = warp == 0 ? sc0 : sc1;
+          const float x = lane < L ? sc[lane] : -INFINITY;
+          const float m = warp_max(x);
+          const float e = lane < L ? expf(x - m) : 0.f;
+          const float sum = warp_sum_xor(e);
+          if (lane < L) sc[lane] = rbf(e / sum);
+        }
+        m2_csync();
+        float outv = 0.f;
+        const int h = (tid >> 7) & 1, d = tid & 127;
+        if (tid < 256) {
+          const float* sc = h == 0 ? sc0 : sc1;
+          float acc = 0.f;
+#pragma unroll
+          for (int j = 0; j < M2_ATT_FAST_L; ++j)
+            if (j < L) acc = fmaf(sc[j], bf2f(Vs[j * 128 + d]), acc);
+          outv = rbf(acc);
+        }
+        const float other = __shfl_xor_sync(0xffffffffu, outv, 1);
+        if (tid < 256 && !(lane & 1))
+          st_slot(reinterpret_cast<u64*>(p.Y) + (((size_t)t * heads + (2 * kvh + h)) * 128 + d >> 1), pack2(outv, other), tag);
+        if (unit + (int)gridDim.x < n_units) m2_csync();
+        continue;
+      }
+      // ---- general path: rows [j_lo, j_hi) (the whole context when the row is not split) ----
+      auto row = [&](const bf16* base, const bf16* cur, const uint2& pre, int j) -> uint2 {
+        if (j == pos) return *reinterpret_cast<const uint2*>(cur + 4 * lane);
+        if (ns == 1 && j == warp) return pre;
+        return __ldcg(reinterpret_cast<const uint2*>(base + (size_t)j * 128 + 4 * lane));
+      };
+      for (int j0 = j_lo + warp; j0 < j_hi; j0 += M2_ATT_U * MEGA_WARPS) {
+        uint2 ku[M2_ATT_U];
+#pragma unroll
+        for (int q = 0; q < M2_ATT_U; ++q) {
+          const int j = j0 + q * MEGA_WARPS;
+          ku[q] = j < j_hi ? row(kbase, kcur, kpre, j) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < M2_ATT_U; ++q) {
+          const int j = j0 + q * MEGA_WARPS;
+          if (j >= j_hi) break;
+          const uint2 u = ku[q];
+          const float k0 = bf_lo(u.x), k1 = bf_hi(u.x), k2 = bf_lo(u.y), k3 = bf_hi(u.y);
+          float d0 = q0[0] * k0 + q0[1] * k1 + q0[2] * k2 + q0[3] * k3;
+          float d1 = q1[0] * k0 + q1[1] * k1 + q1[2] * k2 + q1[3] * k3;
+          d0 = warp_sum_xor(d0);
+          d1 = warp_sum_xor(d1);
+          if (lane == 0) {
+            sc0[j] = rbf(rbf(d0) * scale);
+            sc1[j] = rbf(rbf(d1) * scale);
+          }
+        }
+      }
+      m2_csync();
+      if (warp < 2) {
+        // softmax of head `warp` over the WHOLE context: the maximum and the normaliser are exchanged between the splits of
+        // the item (tagged 8-byte slots, as the activations), so every probability is exp(s - global max) / global sum rounded
+        // to bf16 exactly as in the unsplit kernel; the sum adds the splits' partial sums in split order
+        float* sc = warp == 0 ? sc0 : sc1;
+        float m = -INFINITY;
+        for (int j = j_lo + lane; j < j_hi; j += 32) m = fmaxf(m, sc[j]);
+        m = warp_max(m);
+        if (ns > 1) {
+          if (lane == 0) st_slot(xg + (size_t)split * M2_XCHG_SLOTS + warp, __float_as_uint(m), tag);
+          float mo = -INFINITY;
+          if (lane < ns) {
+            unsigned tries = 0;
+            for (;;) {
+              const u64 sl = ld_slot(xg + (size_t)lane * M2_XCHG_SLOTS + warp);
+              if (slot_tag(sl) == tag) { mo = __uint_as_float(slot_val(sl)); break; }
+              if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 6100000 + (int)gs.epoch); break; }
+            }
+          }
+          m = warp_max(mo);
+        }
+        float sum = 0.f;
+        for (int j = j_lo + lane; j < j_hi; j += 32) {
+          const float e = expf(sc[j] - m);
+          sc[j] = e;
+          sum += e;
+        }
+        sum = warp_sum_xor(sum);
+        if (ns > 1) {
+          if (lane == 0) st_slot(xg + (size_t)split * M2_XCHG_SLOTS + 2 + warp, __float_as_uint(sum), tag);
+          float so = 0.f;
+          if (lane < ns) {
+            unsigned tries = 0;
+            for (;;) {
+              const u64 sl = ld_slot(xg + (size_t)lane * M2_XCHG_SLOTS + 2 + warp);
+              if (slot_tag(sl) == tag) { so = __uint_as_float(slot_val(sl)); break; }
+              if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 6200000 + (int)gs.epoch); break; }
+            }
+          }
+          sum = 0.f;
+          for (int q = 0; q < ns; ++q) sum += __shfl_sync(0xffffffffu, so, q);      // split order
+        }
+        for (int j = j_lo + lane; j < j_hi; j += 32) sc[j] = rbf(sc[j] / sum);
+      }
+      m2_csync();
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int j0 = j_lo + warp; j0 < j_hi; j0 += M2_ATT_U * MEGA_WARPS) {
+        uint2 vu[M2_ATT_U];
+#pragma unroll
+        for (int q = 0; q < M2_ATT_U; ++q) {
+          const int j = j0 + q * MEGA_WARPS;
+          vu[q] = j < j_hi ? row(vbase, vcur, vpre, j) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < M2_ATT_U; ++q) {
+          const int j = j0 + q * MEGA_WARPS;
+          if (j >= j_hi) break;
+          const uint2 u = vu[q];
+          const float v0 = bf_lo(u.x), v1 = bf_hi(u.x), v2 = bf_lo(u.y), v3 = bf_hi(u.y);
+          const float p0 = sc0[j], p1 = sc1[j];
+          o0[0] = fmaf(p0, v0, o0[0]); o0[1] = fmaf(p0, v1, o0[1]); o0[2] = fmaf(p0, v2, o0[2]); o0[3] = fmaf(p0, v3, o0[3]);
+          o1[0] = fmaf(p1, v0, o1[0]); o1[1] = fmaf(p1, v1, o1[1]); o1[2] = fmaf(p1, v2, o1[2]); o1[3] = fmaf(p1, v3, o1[3]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        red[(warp * 2 + 0) * 128 + 4 * lane + i] = o0[i];
+        red[(warp * 2 + 1) * 128 + 4 * lane + i] = o1[i];
+      }
+      m2_csync();
+      {
+        float outv = 0.f;
+        const int h = (tid >> 7) & 1, d = tid & 127;
+        if (tid < 256) {
+          float acc = 0.f;
+#pragma unroll
+          for (int w = 0; w < MEGA_WARPS; ++w) acc += red[(w * 2 + h) * 128 + d];
+          if (ns > 1) {
+            // partial sums of the splits: split s > 0 publishes its 2 x 128 values, split 0 adds them in split order
+            if (split != 0) {
+              st_slot(xg + (size_t)split * M2_XCHG_SLOTS + 4 + tid, __float_as_uint(acc), tag);
+            } else {
+              for (int q = 1; q < ns; ++q) {
+                unsigned tries = 0;
+                for (;;) {
+                  const u64 sl = ld_slot(xg + (size_t)q * M2_XCHG_SLOTS + 4 + tid);
+                  if (slot_tag(sl) == tag) { acc += __uint_as_float(slot_val(sl)); break; }
+                  if (++tries > M2_RETRY_LIMIT) { m2_fail(gs, 6300000 + (int)gs.epoch); break; }
+                }
+              }
+            }
+          }
+          outv = rbf(acc);
+        }
+        const float other = __shfl_xor_sync(0xffffffffu, outv, 1);
+        if (tid < 256 && !(lane & 1) && split == 0)
+          st_slot(reinterpret_cast<u64*>(p.Y) + (((size_t)t * heads + (2 * kvh + h)) * 128 + d >> 1), pack2(outv, other), tag);
+      }
+      m2_csync();
+    }
+  }
+  m2_csync();
+  m2_arrive(gs, p.flags);
+  if (prof_on) prof2(a, 7);
+  return m2_pack(gs);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // 8 consecutive bf16 values -> 4 tagged slots (32 bytes)
 __device__ __forceinline__ void m2_store_row8(u64* dst_slots, const uint4& v, uint32_t tag) {
   st_slot2(dst_slots, v.x, v.y, tag);
@@ -1349,6 +1670,6 @@ static size_t mega2_smem_bytes(const q3_model_desc& d, int B, int max_seq, int g
   if (!ok || n_ph > M2_MAX_PHASES) return 0;
   size_t m = sizeof(SampleSmem);
   m = std::max(m, (size_t)M2_RED_OFF + red_max);
-  m = std::max(m, (size_t)(2 * (std::max(max_seq, d.cp_max_seq) + 3) + 256 + 16 * 2 * 128) * 4 + (2 * M2_ATT_FAST_L * 128 + 256) * 2);
+  m = std::max(m, (size_t)(2 * (std::max(max_seq, d.cp_max_seq) + 3) + 256 + 16 * 2 * 128) * 4 + (2 * M2_ATT_FAST_L * 128 + 256) * 2 + 256);
   return (((size_t)n_ph * sizeof(M2Phase) + 127) & ~(size_t)127) + m;
 }

@@ -70,9 +70,10 @@ struct q3_session {
   int mega_ver = 2;                // 1: fence-based grid barriers (mega.cuh), 2: tagged dataflow phases (mega2.cuh)
   DBuf tr_ids, tr_proj;            // staging of q3_set_trailing_ids
   int stream_first = 0;            // q3_session_set_first_chunk: frames of the first streamed chunk (0 = chunk_frames)
+  int split_thr = 0;               // split-KV attention: context length from which a row is cut over M2_SPLIT_NS CTAs (0 = never)
   DBuf pf_tid, pf_cid;             // staging of q3_prefill_ids
   DBuf pf_spk, pf_ref;             // q3_prefill_voice_clone: speaker embeddings, reference codes
-  DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag;
+  DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag, m2_xchg;
   std::vector<DBuf> m2_progs;      // cached full-frame program of every row group
   std::vector<int> m2_group_nph;
   int m2_n_ph = 0;                 // phases of the cached full-frame program (0: not built)
@@ -585,6 +586,18 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
   return pr;
 }
 
+// Split-KV attention (m2_attn_units, mega2.cuh): rows whose context has reached `thr` positions are cut over M2_SPLIT_NS CTAs.
+// The kernel takes the unit-mapped path only in launches in which some row CAN reach the threshold (contexts grow by one
+// position per frame): frames_end = frames generated when the launch ends.  Whether a given row is split depends on its own
+// context length only.  Q3_SPLIT_KV = threshold in positions (default 512), 0 = never.
+static int split_kv_threshold(const q3_session* s, int frames_end) {
+  const int thr = s->split_thr;                  // read from Q3_SPLIT_KV when the session was created
+  if (thr <= M2_ATT_FAST_L || !s->m2_xchg.p) return 0;
+  int max_len = 0;
+  for (int b = 0; b < s->B; ++b) max_len = std::max(max_len, s->prefill_len[b]);
+  return max_len + frames_end + 1 >= thr ? thr : 0;
+}
+
 static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   const q3_model* m = s->m;
   const q3_model_desc& d = m->d;
@@ -628,6 +641,8 @@ static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   const char* e4 = std::getenv("Q3_RING_SHIFT");
   a.ring_shift = e4 ? std::min(3, std::max(0, std::atoi(e4))) : 3;
   a.m4_slots = s->mega_ver == 5 ? s->m5_slots : s->m4_slots; a.m4_red2 = s->m4_red2;
+  a.xchg = s->m2_xchg.as<u64>();
+  a.split_min_l = split_kv_threshold(s, s->frames_run + 17);      // callers that know the launch's last frame set it exactly
   return a;
 }
 
@@ -706,6 +721,7 @@ static void run_frames_mega2(q3_session* s, int n) {
       const int r0 = gi * MEGA_TMAX, Bg = std::min(MEGA_TMAX, s->B - r0);
       M2Args a = mega2_args(s, r0, Bg);
       a.n_frames = todo; a.do_sample = 1;
+      a.split_min_l = split_kv_threshold(s, s->frames_run + done_frames + todo);
       mega2_launch(s, a, s->m2_progs[gi], s->m2_group_nph[gi]);
     }
     done_frames += todo;
@@ -1067,6 +1083,7 @@ static void reset_state(q3_session* s, const uint64_t* seeds) {
     const unsigned one = 1;
     Q3_CHECK_CUDA(cudaMemcpyAsync(s->m2_tag.p, &one, 4, cudaMemcpyHostToDevice, s->st));
     s->m2_x.zero(s->st); s->m2_qkv.zero(s->st); s->m2_attn.zero(s->st); s->m2_h1.zero(s->st); s->m2_act.zero(s->st);
+    if (s->m2_xchg.p) s->m2_xchg.zero(s->st);      // the exchange slots of m2_attn_units carry the same tags
     Q3_CHECK_CUDA(cudaStreamSynchronize(s->st));
   }
   std::fill(s->prefill_len.begin(), s->prefill_len.end(), 0);
@@ -1169,6 +1186,12 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
         const size_t qdm = (size_t)std::max(d.heads, d.cp_heads) * 128;
         s->m2_x.alloc(MEGA_TMAX * Hm * 4); s->m2_qkv.alloc(MEGA_TMAX * nhm * 4); s->m2_attn.alloc(MEGA_TMAX * qdm * 4);
         s->m2_h1.alloc(MEGA_TMAX * Hm * 8); s->m2_act.alloc(MEGA_TMAX * Im * 4); s->m2_tag.alloc(64);
+        s->m2_xchg.alloc((size_t)MEGA_TMAX * d.kv_heads * M2_SPLIT_NS * M2_XCHG_SLOTS * 8);
+        s->m2_xchg.zero();
+        {
+          const char* e8 = std::getenv("Q3_SPLIT_KV");
+          s->split_thr = e8 ? std::atoi(e8) : 512;
+        }
         s->m2_x.zero(); s->m2_qkv.zero(); s->m2_attn.zero(); s->m2_h1.zero(); s->m2_act.zero();
         const unsigned one = 1;
         Q3_CHECK_CUDA(cudaMemcpy(s->m2_tag.p, &one, 4, cudaMemcpyHostToDevice));

@@ -261,7 +261,8 @@ def test_eos_row_follows_the_oracle_to_its_last_frame():
 def test_long_context_voice_design_prefill_follows_the_oracle():
     """Long context at BASELINE dimensions (0.6B: 28 layers, 16 query / 8 kv heads): a VoiceDesign prompt whose 700 instruct
     ids sit in the prefill (talker.rs:585-627: context = 700 + 9 positions before the first frame), batch 2 with one short
-    row, then 3 decode frames -- the prefill attention, the decode attention over ~710 cached positions of 8 kv heads and the
+    row, then 3 decode frames -- the prefill attention, the decode attention over ~710 cached positions of 8 kv heads (above the
+    split-KV threshold of 512: the long row's attention runs cut over 4 CTAs, m2_attn_units, the short row's unsplit) and the
     RoPE table far from position 0 are held to the oracle by the same six checks."""
     spec = S.SPEC_0_6B
     F = 3
@@ -272,6 +273,12 @@ def test_long_context_voice_design_prefill_follows_the_oracle():
     seeds = [7, 8]
     tts = gpu_tts(spec)
     tapped, taps = run_tapped(tts, prompts, seeds, opts, F, instruct)
+    # one frame per launch (tapped) == 16 frames per launch (production) at a split-KV context as well
+    pp = [tts.voice_design_prompt(t, ins, "english") for t, ins in zip(prompts, instruct)]
+    sess = tts._new_session(prompts, pp, opts, seeds, max_seq=max(len(p[0]) for p in pp) + F + 40)
+    codes, n = sess.generate(F)
+    sess.close()
+    assert [codes[b, : n[b]].tolist() for b in range(2)] == tapped
     rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=(0, 1), tapped=tapped, taps=taps, instruct=instruct)
     print("follow report:", rep)
     assert rep["frames"] == 2 * F and rep["sample_exempt"] == 0
@@ -304,3 +311,44 @@ def test_voice_clone_prompts_follow_the_oracle(spec):
     rep = check_follow(spec, tts, prompts, seeds, opts, F, rows=(0, 1, 2), tapped=tapped, taps=taps, clone=clone)
     print("follow report:", rep)
     assert rep["frames"] == 3 * F and rep["sample_exempt"] == 0
+
+
+def test_split_kv_attention_is_row_independent_and_the_unsplit_form_is_untouched(monkeypatch):
+    """Split-KV decode attention (m2_attn_units): rows whose context has reached the threshold are cut over 4 CTAs that
+    exchange the softmax maximum / normaliser and their partial P*V sums.  (a) With the unit-mapped path active but no row
+    long enough to be split, the codes are those of the unsplit kernel, bit for bit; (b) with splitting on, a batch that
+    mixes long and short rows is deterministic and every row equals its batch-1 run (whether a row is split depends on its
+    own context only).  The comparison with the oracle at a split context is
+    test_long_context_voice_design_prefill_follows_the_oracle (710 positions >= the default threshold of 512)."""
+    spec = S.SPEC_RING
+    tts = gpu_tts(spec)
+    F = 20
+    g = torch.Generator().manual_seed(17)
+    prompts = [W.synthetic_prompt(i, spec) for i in range(4)]
+    instr = [torch.randint(0, 1500, (n,), generator=g).tolist() for n in (640, 9, 580, 30)]
+    pp = [tts.voice_design_prompt(t, ins, "english") for t, ins in zip(prompts, instr)]
+    opts = api.SynthesisOptions(max_length=F, eos_token_id=None)
+
+    def run(rows):
+        sess = api.Session(tts.model, len(rows), opts, [42 + r for r in rows], max_seq=640 + F + 64)
+        sess.prefill_ids([pp[r][0] for r in rows], [pp[r][1] for r in rows])
+        sess.set_trailing_ids([list(prompts[r][1:]) for r in rows])
+        codes, n = sess.generate(F)
+        sess.close()
+        return codes
+
+    monkeypatch.setenv("Q3_SPLIT_KV", "0")
+    unsplit = run([0, 1, 2, 3])
+    monkeypatch.setenv("Q3_SPLIT_KV", "100000")          # unit-mapped path, nothing long enough to split
+    assert np.array_equal(run([0, 1, 2, 3]), unsplit)
+    monkeypatch.setenv("Q3_SPLIT_KV", "512")
+    split = run([0, 1, 2, 3])
+    assert np.array_equal(run([0, 1, 2, 3]), split)       # deterministic
+    assert np.array_equal(split[1], unsplit[1]) and np.array_equal(split[3], unsplit[3])     # short rows: untouched
+    for r in range(4):
+        assert np.array_equal(run([r])[0], split[r]), ("row differs from its batch-1 run", r)
+    # the threshold is crossed inside the run: 505 + 9 prefill positions, 20 frames
+    instr2 = torch.randint(0, 1500, (495,), generator=g).tolist()
+    pp[0] = tts.voice_design_prompt(prompts[0], instr2, "english")
+    a, b2 = run([0, 1]), run([0])
+    assert np.array_equal(a[0], b2[0])
