@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(M4_THREADS, 1) decode_frames_mega4_kernel(cons
 static size_t mega4_smem_bytes(const q3_model_desc& d, int B, int max_seq, int* n_slots, int* red2) {
   (void)B;
   const size_t red = (size_t)2 * 2 * 8 * M4_RED_CS * 4;
-  const size_t attn = (size_t)(2 * (std::max(max_seq, d.cp_max_seq) + 3) + 256 + 16 * 2 * 128) * 4 + (2 * M2_ATT_FAST_L * 128 + 256) * 2;
+  const size_t attn = (size_t)(2 * (std::max(max_seq, d.cp_max_seq) + 3) + 256 + 16 * 2 * 128) * 4 + (2 * M2_ATT_FAST_L * 128 + 256) * 2 + 256;      // + the row tables of m2_attn_units
   const size_t avail = 227 * 1024 - 5120;          // static shared memory of the kernel: M4Shared (4 KB) + profiling index
   size_t work = std::max(std::max((size_t)M2_RED_OFF + red, attn), sizeof(SampleSmem));
   *red2 = 1;
