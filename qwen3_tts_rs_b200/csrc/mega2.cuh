@@ -1197,7 +1197,10 @@ __device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phas
 // (~40 us per layer); here up to 4 x 8 x B CTAs share them.  The current position's K / V rows are appended by the last
 // split only; every other cache row was written at least one frame (549 phases, several of them release / acquire
 // barriers) earlier, by whichever CTA owned the position then.
-constexpr int M2_SPLIT_NS = 4;
+#ifndef M2_SPLIT_NS_DEF
+#define M2_SPLIT_NS_DEF 4
+#endif
+constexpr int M2_SPLIT_NS = M2_SPLIT_NS_DEF;
 constexpr int M2_XCHG_SLOTS = 4 + 256;          // per split: max[2], sum[2], partial P*V [2][128]
 __device__ __noinline__ unsigned long long m2_attn_units(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
                                                          const uint32_t tag) {

@@ -15,7 +15,7 @@ from .spec import ModelSpec
 HERE = os.path.dirname(os.path.abspath(__file__))
 # Q3TTS_LIB=dev selects the development library (historical kernel generations + profiling hooks, build.py); read once, at
 # the first load of the process
-LIB_PATH = os.path.join(HERE, "libq3tts_b200_dev.so" if os.environ.get("Q3TTS_LIB") == "dev" else "libq3tts_b200.so")
+LIB_PATH = os.environ.get("Q3TTS_LIB_PATH") or os.path.join(HERE, "libq3tts_b200_dev.so" if os.environ.get("Q3TTS_LIB") == "dev" else "libq3tts_b200.so")
 IS_DEV = os.environ.get("Q3TTS_LIB") == "dev"
 
 Q3_BF16, Q3_F32 = 0, 1
