@@ -90,8 +90,9 @@ struct M2Args {
   int pf_sleep;         // ring kernel: nanoseconds the producer warp sleeps between polls of a full ring
   int m4_slots;         // mega4.cuh: ring slots in use
   int m4_red2;          // mega4.cuh: the combine buffer is double-buffered over tiles
-  u64* xchg;            // m2_attn_units: exchange slots of the splits of a long row, [rows x kv_heads x M2_SPLIT_NS][M2_XCHG_SLOTS]
+  u64* xchg;            // m2_attn_units: exchange slots of the splits of a long row, [rows x kv_heads x split_ns][M2_XCHG_SLOTS]
   int split_min_l;      // > 0: talker attention of this launch runs m2_attn_units, rows with >= split_min_l positions are split
+  int split_ns;         // ... over this many CTAs (<= M2_SPLIT_NS_MAX)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -1190,17 +1191,14 @@ __device__ __noinline__ unsigned long long m2_attn(const M2Args& a, const M2Phas
 // Split-KV form of the talker's decode attention (one token per row), used for the launches in which some row's context can
 // reach a.split_min_l positions (host decision, q3tts.cu mega2_launch).  A row whose context is shorter takes exactly the
 // code path of m2_attn (same row order per warp, same reduction trees: bit-identical results); a longer row is cut into
-// M2_SPLIT_NS ranges of cache rows handled by M2_SPLIT_NS CTAs, which exchange the softmax maximum, the normaliser and
+// a.split_ns (4) ranges of cache rows handled by as many CTAs, which exchange the softmax maximum, the normaliser and
 // their partial P*V sums through tagged slots in global memory (a.xchg).  Whether a row is split depends on ITS context
 // length only, never on the other rows of the batch, so a row of a batch still equals its batch-1 run bit for bit.
 // At 2000 positions m2_attn is bound by the latency of its batches of cache rows on the 8 x B CTAs that have work
 // (~40 us per layer); here up to 4 x 8 x B CTAs share them.  The current position's K / V rows are appended by the last
 // split only; every other cache row was written at least one frame (549 phases, several of them release / acquire
 // barriers) earlier, by whichever CTA owned the position then.
-#ifndef M2_SPLIT_NS_DEF
-#define M2_SPLIT_NS_DEF 4
-#endif
-constexpr int M2_SPLIT_NS = M2_SPLIT_NS_DEF;
+constexpr int M2_SPLIT_NS_MAX = 8;            // a.split_ns: 4 by default, Q3_SPLIT_NS=8 for single-stream long-form (host, q3tts.cu)
 constexpr int M2_XCHG_SLOTS = 4 + 256;          // per split: max[2], sum[2], partial P*V [2][128]
 __device__ __noinline__ unsigned long long m2_attn_units(const M2Args& a, const M2Phase& p, unsigned char* smem, M2Sync gs,
                                                          const uint32_t tag) {
@@ -1233,7 +1231,7 @@ __device__ __noinline__ unsigned long long m2_attn_units(const M2Args& a, const 
   m2_csync();
   if (tid == 0) {
     int u = 0;
-    for (int r = 0; r < n_rows; ++r) { s_ub[r] = u; u += kv_heads * (s_L[r] >= a.split_min_l ? M2_SPLIT_NS : 1); }
+    for (int r = 0; r < n_rows; ++r) { s_ub[r] = u; u += kv_heads * (s_L[r] >= a.split_min_l ? a.split_ns : 1); }
     s_ub[n_rows] = u;
   }
   m2_csync();
@@ -1242,7 +1240,7 @@ __device__ __noinline__ unsigned long long m2_attn_units(const M2Args& a, const 
     int b = 0;
     while (b + 1 < n_rows && s_ub[b + 1] <= unit) ++b;
     const int L = s_L[b], pos = L - 1;
-    const int ns = L >= a.split_min_l ? M2_SPLIT_NS : 1;
+    const int ns = L >= a.split_min_l ? a.split_ns : 1;
     const int ru = unit - s_ub[b], kvh = ru / ns, split = ru - kvh * ns;
     bf16* kbase = const_cast<bf16*>(p.W) + ((size_t)b * kv_heads + kvh) * max_seq * 128;
     bf16* vbase = const_cast<bf16*>(p.W2) + ((size_t)b * kv_heads + kvh) * max_seq * 128;

@@ -70,7 +70,7 @@ struct q3_session {
   int mega_ver = 2;                // 1: fence-based grid barriers (mega.cuh), 2: tagged dataflow phases (mega2.cuh)
   DBuf tr_ids, tr_proj;            // staging of q3_set_trailing_ids
   int stream_first = 0;            // q3_session_set_first_chunk: frames of the first streamed chunk (0 = chunk_frames)
-  int split_thr = 0;               // split-KV attention: context length from which a row is cut over M2_SPLIT_NS CTAs (0 = never)
+  int split_thr = 0, split_ns = 4; // split-KV attention: context length from which a row is cut over split_ns CTAs (0 = never)
   DBuf pf_tid, pf_cid;             // staging of q3_prefill_ids
   DBuf pf_spk, pf_ref;             // q3_prefill_voice_clone: speaker embeddings, reference codes
   DBuf m2_x, m2_qkv, m2_attn, m2_h1, m2_act, m2_prog, m2_prog_tmp, m2_tag, m2_xchg;
@@ -586,7 +586,7 @@ static std::vector<M2Phase> m2_build_program(q3_session* s, bool do_cp, bool do_
   return pr;
 }
 
-// Split-KV attention (m2_attn_units, mega2.cuh): rows whose context has reached `thr` positions are cut over M2_SPLIT_NS CTAs.
+// Split-KV attention (m2_attn_units, mega2.cuh): rows whose context has reached `thr` positions are cut over split_ns CTAs.
 // The kernel takes the unit-mapped path only in launches in which some row CAN reach the threshold (contexts grow by one
 // position per frame): frames_end = frames generated when the launch ends.  Whether a given row is split depends on its own
 // context length only.  Q3_SPLIT_KV = threshold in positions (default 512), 0 = never.
@@ -643,6 +643,7 @@ static M2Args mega2_args(q3_session* s, int r0 = 0, int Bg = -1) {
   a.m4_slots = s->mega_ver == 5 ? s->m5_slots : s->m4_slots; a.m4_red2 = s->m4_red2;
   a.xchg = s->m2_xchg.as<u64>();
   a.split_min_l = split_kv_threshold(s, s->frames_run + 17);      // callers that know the launch's last frame set it exactly
+  a.split_ns = s->split_ns;
   return a;
 }
 
@@ -1186,11 +1187,16 @@ q3_status q3_session_create(const q3_model* m, int32_t batch, int32_t max_seq, c
         const size_t qdm = (size_t)std::max(d.heads, d.cp_heads) * 128;
         s->m2_x.alloc(MEGA_TMAX * Hm * 4); s->m2_qkv.alloc(MEGA_TMAX * nhm * 4); s->m2_attn.alloc(MEGA_TMAX * qdm * 4);
         s->m2_h1.alloc(MEGA_TMAX * Hm * 8); s->m2_act.alloc(MEGA_TMAX * Im * 4); s->m2_tag.alloc(64);
-        s->m2_xchg.alloc((size_t)MEGA_TMAX * d.kv_heads * M2_SPLIT_NS * M2_XCHG_SLOTS * 8);
+        s->m2_xchg.alloc((size_t)MEGA_TMAX * d.kv_heads * M2_SPLIT_NS_MAX * M2_XCHG_SLOTS * 8);
         s->m2_xchg.zero();
         {
           const char* e8 = std::getenv("Q3_SPLIT_KV");
           s->split_thr = e8 ? std::atoi(e8) : 512;
+          // 4 splits by default; 8 (Q3_SPLIT_NS=8) suit a single long-form stream (+10 % at batch 1, -9 % at batch 8, 1536
+          // frames).  The count is part of the numerics (summation order), so it is a session setting, never derived from
+          // the batch: a row equals its batch-1 run under the same setting.
+          const char* e9 = std::getenv("Q3_SPLIT_NS");
+          s->split_ns = e9 ? std::max(2, std::min((int)M2_SPLIT_NS_MAX, std::atoi(e9))) : 4;
         }
         s->m2_x.zero(); s->m2_qkv.zero(); s->m2_attn.zero(); s->m2_h1.zero(); s->m2_act.zero();
         const unsigned one = 1;
