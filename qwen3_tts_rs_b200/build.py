@@ -29,8 +29,9 @@ def _stale(target: str, deps) -> bool:
 
 
 # Two libraries from the same sources:
-#   libq3tts_b200.so      the product: the dataflow kernel (mega2.cuh) and the TMA-ring kernel (mega4.cuh) only, profiling
-#                         hooks compiled out (code that never runs still costs instruction fetch in a run-once-per-phase kernel)
+#   libq3tts_b200.so      the product: the dataflow kernel (mega2.cuh, the default) and the two TMA-fed generations (mega4.cuh,
+#                         mega5.cuh, opt-in), profiling hooks compiled out (code that never runs still costs instruction fetch
+#                         in a run-once-per-phase kernel)
 #   libq3tts_b200_dev.so  + the historical generations (Q3_MEGA=1 / 3) and the profiling hooks (tools/profile_*.py, and the
 #                         tests that keep the old generations against the oracle); selected with Q3TTS_LIB=dev
 VARIANTS = {"": [], "_dev": ["-DQ3_ALL_GENERATIONS=1", "-DQ3_PROF=1"]}
